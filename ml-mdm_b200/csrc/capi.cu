@@ -1,0 +1,38 @@
+// extern "C" surface of libmdm_b200.so (declared in include/mdm_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "gemm_tc.cuh"
+#include "mdm_b200.h"
+
+namespace mdm {
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+}  // namespace mdm
+
+extern "C" {
+
+const char* mdm_last_error(void) { return mdm::g_err.c_str(); }
+int mdm_version(void) { return 100; }
+unsigned long long mdm_launch_count(void) { return mdm::g_launch_count; }
+
+int mdm_gemm_raw(const mdm_tmap_spec* A, const mdm_tmap_spec* B, int a_mn, int b_mn,
+                 const mdm_gemm_params* p, mdm_stream_t stream) {
+  int rc = mdm::launch_gemm(*A, *B, a_mn, b_mn, *p, static_cast<cudaStream_t>(stream));
+  if (rc != 0) {
+    mdm::set_error("mdm_gemm_raw: launch failed (%d: %s)", rc,
+                   rc > 0 ? cudaGetErrorString(static_cast<cudaError_t>(rc)) : "invalid arguments");
+    return rc > 0 ? -rc : rc;
+  }
+  return 0;
+}
+}
