@@ -75,6 +75,88 @@ typedef struct mdm_gemm_params {
 int mdm_gemm_raw(const mdm_tmap_spec* A, const mdm_tmap_spec* B, int a_mn, int b_mn,
                  const mdm_gemm_params* p, mdm_stream_t stream);
 
+
+/* ---------------------------------------------------------------- the (nested) U-Net denoiser */
+
+#define MDM_MAX_RES 8
+#define MDM_MAX_LEVELS 4
+
+/* One U-Net of the nest.  Field meaning follows UNetConfig (models/unet.py:62-156) after
+ * __post_init__: lists are per resolution; num_attn[i] is already 0 when i is not in
+ * attention_levels; cond_level[i] = 1 when i is in attention_levels. */
+typedef struct mdm_level_cfg {
+  int32_t num_res;
+  int32_t channels[MDM_MAX_RES];
+  int32_t num_resnets[MDM_MAX_RES];
+  int32_t num_attn[MDM_MAX_RES];
+  int32_t cond_level[MDM_MAX_RES];
+  int32_t temporal_dim;
+  int32_t groups;
+  int32_t use_attention_ffn;
+  int32_t skip_mid_blocks;
+  int32_t nesting;            /* this U-Net sits inside another one (UNetConfig.nesting) */
+  int32_t skip_normalization; /* NestedUNetConfig.skip_normalization (outer levels only) */
+  int32_t has_micro_scale;    /* micro_conditioning == "scale:<default>" */
+  float micro_scale_default;
+} mdm_level_cfg;
+
+typedef struct mdm_net_cfg {
+  int32_t num_levels; /* 1: UNet; >1: NestedUNet, levels[0] outermost (nested_unet.py:96-160) */
+  mdm_level_cfg levels[MDM_MAX_LEVELS];
+  int32_t in_channels, out_channels;
+  int32_t lm_dim;      /* width of lm_outputs */
+  int32_t cond_dim;    /* width seen by cross-attention (conditioning_feature_proj_dim when projecting) */
+  int32_t has_lm_proj; /* unet.py:760-765 */
+  int32_t has_cond_emb;
+  int32_t masked_cross_attention;
+  int32_t num_heads; /* 8 (unet.py:245) */
+} mdm_net_cfg;
+
+typedef struct mdm_net mdm_net;
+
+int mdm_net_create(const mdm_net_cfg* cfg, mdm_net** out);
+void mdm_net_destroy(mdm_net* net);
+
+/* Parameter table: same names and shapes as the reference module's state_dict() (OIHW fp32). */
+int mdm_net_num_params(const mdm_net* net);
+int mdm_net_param_info(const mdm_net* net, int index, const char** name, int32_t* ndim, int64_t shape[4]);
+/* Bind caller-owned fp32 storage. grad may be NULL (no gradient wanted); gradients are ACCUMULATED
+ * (+=) into it by mdm_net_backward.  Pointers are borrowed until rebound. */
+int mdm_net_bind_param(mdm_net* net, const char* name, void* weight, void* grad);
+/* Tell the engine the fp32 weights changed (optimizer step / load): fp16 operand copies are rebuilt
+ * at the next forward. */
+int mdm_net_weights_changed(mdm_net* net);
+
+typedef struct mdm_net_io {
+  int32_t batch;
+  int32_t tokens;
+  int32_t res[MDM_MAX_LEVELS];      /* image side per level, outermost (largest) first */
+  const float* x_t[MDM_MAX_LEVELS]; /* NCHW fp32, (batch, in_channels, res, res) */
+  const int64_t* times;             /* (batch,) */
+  const float* lm;                  /* (batch, tokens, lm_dim) fp32 */
+  const float* lm_mask;             /* (batch, tokens) fp32 0/1, or NULL */
+  const float* micro_scale;         /* (batch,) fp32 or NULL => per-level default (unet.py:924) */
+  float* out[MDM_MAX_LEVELS];       /* NCHW fp32 predictions, same shapes as x_t */
+  int32_t save_for_backward;
+} mdm_net_io;
+
+/* UNet.forward / NestedUNet.forward (unet.py:971-987). */
+int mdm_net_forward(mdm_net* net, const mdm_net_io* io, mdm_stream_t stream);
+
+typedef struct mdm_net_grad_io {
+  const float* dout[MDM_MAX_LEVELS]; /* d loss / d out[l], NCHW fp32; NULL => zero */
+} mdm_net_grad_io;
+
+/* Backward of the last mdm_net_forward(save_for_backward=1): accumulates parameter gradients. */
+int mdm_net_backward(mdm_net* net, const mdm_net_grad_io* gio, mdm_stream_t stream);
+
+/* Device bytes currently reserved by the engine's pool / its high-water mark of live bytes. */
+uint64_t mdm_net_workspace_bytes(const mdm_net* net);
+uint64_t mdm_net_workspace_high_water(const mdm_net* net);
+/* Debug: copy a named fp32 intermediate of the last forward (e.g. "down_blocks.0.0") to dst.
+ * Returns its element count, or negative if unknown. Layout NHWC. */
+int64_t mdm_net_debug_fetch(mdm_net* net, const char* name, float* dst, int64_t max_elems, mdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

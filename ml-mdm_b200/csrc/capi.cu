@@ -4,6 +4,7 @@
 
 #include <string>
 
+#include "engine.cuh"
 #include "gemm_tc.cuh"
 #include "mdm_b200.h"
 

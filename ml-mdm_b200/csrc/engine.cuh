@@ -1,0 +1,127 @@
+// Host-side engine of the denoising path: device memory pool, parameter table, GEMM/conv wrappers
+// and the backward tape.  The network definition itself lives in net.cu.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <deque>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace mdm {
+
+void set_error(const char* fmt, ...);
+
+struct MdmFail : public std::runtime_error {
+  explicit MdmFail(const std::string& m) : std::runtime_error(m) {}
+};
+#define MDM_CHECK(cond, msg)                                                             \
+  do {                                                                                   \
+    if (!(cond)) throw ::mdm::MdmFail(std::string(msg) + " [" #cond "] at " __FILE__ ":" + \
+                                      std::to_string(__LINE__));                         \
+  } while (0)
+#define MDM_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      throw ::mdm::MdmFail(std::string("CUDA error: ") + cudaGetErrorString(e__) + " in " #call + \
+                           " at " __FILE__ ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+// Size-class caching allocator. Blocks are handed out per step and all returned by reset();
+// after the first step with a given shape no cudaMalloc happens on the hot path.
+class Pool {
+ public:
+  ~Pool();
+  void* alloc(size_t bytes);
+  void release(void* p);  // early return of a temporary
+  void reset();           // every live block becomes free
+  void trim();            // cudaFree everything
+  size_t reserved() const { return reserved_; }
+  size_t high_water() const { return high_; }
+
+ private:
+  std::unordered_map<size_t, std::vector<void*>> free_;
+  std::unordered_map<void*, size_t> size_of_;
+  std::unordered_map<void*, bool> live_;
+  size_t reserved_ = 0, in_use_ = 0, high_ = 0;
+};
+
+// fp32 NHWC activation on the residual stream (or any fp32 node that receives gradients).
+struct Act {
+  float* p = nullptr;
+  float* g = nullptr;  // gradient (same shape), allocated on first contribution
+  bool ginit = false;
+  int n = 0, h = 0, w = 0, c = 0;
+  long long numel() const { return static_cast<long long>(n) * h * w * c; }
+  long long rows() const { return static_cast<long long>(n) * h * w; }
+};
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+  float* w = nullptr;  // bound fp32 master weights (owned by the caller)
+  float* g = nullptr;  // bound fp32 gradient buffer (owned by the caller), may be null
+  __half* w16 = nullptr;  // packed fp16 operand copy (owned by the engine), null if not a GEMM weight
+  int pack = 0;           // 0 none, 1 plain cast, 2 conv [Co][taps][Ci], 3 conv_in [Co][32]
+};
+
+struct Epi {
+  float alpha = 1.f;
+  const float* alpha_dev = nullptr;
+  const float* bias = nullptr;
+  const float* residual = nullptr;
+  float* out_f32 = nullptr;
+  __half* out_f16 = nullptr;
+  __half* out_act_f16 = nullptr;
+  int act = 0;
+  long long ldc = 0;  // 0: dense
+  bool atomic_ok = false;  // out_f32 is zero-initialised (or accumulating) and split-K may be used
+};
+
+struct Engine {
+  cudaStream_t st = nullptr;
+  Pool pool;
+  bool training = false;
+  std::vector<std::function<void()>> tape;
+  std::deque<Act> acts;
+  // device scalars for gradient scaling
+  float* d_scale = nullptr;
+  float* d_inv_scale = nullptr;
+  float* d_amax = nullptr;
+
+  template <typename T>
+  T* alloc(long long n) {
+    return static_cast<T*>(pool.alloc(static_cast<size_t>(n) * sizeof(T)));
+  }
+  float* zeros_f32(long long n);
+  Act* new_act(int n, int h, int w, int c, bool alloc_data = true);
+  // returns the gradient buffer of `a` and whether the caller must accumulate (1) or overwrite (0)
+  float* grad_buf(Act* a, int* acc);
+
+  // ---- GEMM wrappers (fp16 operands)
+  // C[M,N] = A[M,K] * W[N,K]^T
+  void gemm_nt(const __half* A, long long lda, const __half* W, long long ldw, int M, int N, int K, const Epi& e);
+  // C[M,N] = A[M,K] * Bm[K,N]      (Bm row-major, i.e. MN-major operand)
+  void gemm_nn(const __half* A, long long lda, const __half* Bm, long long ldb, int M, int N, int K, const Epi& e);
+  // C[M,N] = At[K,M]^T * Bm[K,N]   (both MN-major; contraction over rows)
+  void gemm_tn(const __half* At, long long lda, const __half* Bm, long long ldb, int M, int N, int K, const Epi& e);
+  // 3x3 / pad 1 / stride 1 conv over NHWC fp16 x (channel stride ldx), packed weights [Cout][9][Cin]
+  void conv3x3_fwd(const __half* x16, int ldx, int N, int H, int W, int Cin, const __half* w16, int Cout,
+                   const Epi& e);
+  void conv3x3_dgrad(const __half* dy16, int ldy, int N, int H, int W, int Cout, const __half* w16, int Cin,
+                     const Epi& e);
+  // packed_out: [Cout][9][Cin] fp32, overwritten
+  void conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int Cin,
+                     int Cout, float* packed_out);
+};
+
+}  // namespace mdm

@@ -1,0 +1,1139 @@
+// Streaming (HBM-bound) kernels of the denoising path. See kernels.cuh for the contracts.
+#include "kernels.cuh"
+
+#include <math.h>
+
+#include "gemm_tc.cuh"  // g_launch_count
+
+namespace mdm {
+namespace {
+
+constexpr int TPB = 256;
+constexpr int NL = 6;  // float4 channel lanes per thread (C <= 4 * TPB * NL)
+constexpr float GN_EPS = 1e-5f;
+
+#define MDM_LAUNCHED() (++g_launch_count)
+
+__host__ __device__ inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// Thread -> (channel lane, pixel sub-slot) mapping shared by the per-channel streaming kernels.
+// C/4 float4 "lanes" per pixel. When lanes <= TPB several pixels are processed per pass.
+struct LaneMap {
+  int lanes, ppi, t_lane, stride, sub;
+  bool active;
+};
+__device__ __forceinline__ LaneMap lane_map(int C) {
+  LaneMap m;
+  m.lanes = C >> 2;
+  if (m.lanes <= TPB) {
+    m.ppi = TPB / m.lanes;
+    m.t_lane = threadIdx.x % m.lanes;
+    m.sub = threadIdx.x / m.lanes;
+    m.active = m.sub < m.ppi;
+    m.stride = m.lanes;  // only j == 0 is in range
+  } else {
+    m.ppi = 1;
+    m.t_lane = threadIdx.x;
+    m.sub = 0;
+    m.active = true;
+    m.stride = TPB;
+  }
+  return m;
+}
+
+__device__ __forceinline__ float4 ld_src(const Src2& s, long long pix, int c) {
+  if (c < s.c0) return __ldg(reinterpret_cast<const float4*>(s.p0 + pix * s.c0 + c));
+  return __ldg(reinterpret_cast<const float4*>(s.p1 + pix * s.c1 + (c - s.c0)));
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = sigmoidf_(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ void st_half4(__half* p, float a, float b, float c, float d) {
+  __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo);
+  v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+
+inline int pixel_chunks(int N, int HW, int ppi_hint) {
+  long long want = cdiv(4 * 148, N);
+  long long maxc = cdiv(HW, ppi_hint > 0 ? ppi_hint : 1);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  return static_cast<int>(want);
+}
+inline int host_ppi(int C) {
+  int lanes = C / 4;
+  return lanes <= TPB ? TPB / lanes : 1;
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+__global__ void __launch_bounds__(TPB) gn_stats_kernel(Src2 x, int HW, int G, float* __restrict__ sums) {
+  const int C = x.c0 + x.c1;
+  const int cpg = C / G;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(HW, gridDim.x));
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  float4 s[NL], q[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    s[j] = make_float4(0, 0, 0, 0);
+    q[j] = make_float4(0, 0, 0, 0);
+  }
+  if (m.active) {
+    for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
+      const long long pix = static_cast<long long>(n) * HW + p;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const int l = m.t_lane + j * m.stride;
+        if (l < m.lanes) {
+          const float4 v = ld_src(x, pix, 4 * l);
+          s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
+          q[j].x += v.x * v.x; q[j].y += v.y * v.y; q[j].z += v.z * v.z; q[j].w += v.w * v.w;
+        }
+      }
+    }
+  }
+  __shared__ float gs[128], gq[128];
+  for (int i = threadIdx.x; i < G; i += TPB) {
+    gs[i] = 0.f;
+    gq[i] = 0.f;
+  }
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        const int c = 4 * l;
+        const float sv[4] = {s[j].x, s[j].y, s[j].z, s[j].w};
+        const float qv[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          atomicAdd(&gs[(c + k) / cpg], sv[k]);
+          atomicAdd(&gq[(c + k) / cpg], qv[k]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += TPB) {
+    atomicAdd(&sums[(static_cast<long long>(n) * G + g) * 2 + 0], gs[g]);
+    atomicAdd(&sums[(static_cast<long long>(n) * G + g) * 2 + 1], gq[g]);
+  }
+}
+
+// Per-thread GroupNorm coefficients of its channel lanes: xhat = x*rs + (-mean*rs); u = xhat*ga + be
+// with ga = gamma*(1+ta), be = beta*(1+ta)+tb.
+struct GnCoef {
+  float4 rs[NL], nm[NL], ga[NL], be[NL];
+};
+__device__ __forceinline__ void gn_coefs(GnCoef& k, const LaneMap& m, int n, int C, int G, int HW,
+                                         const float* sums, const float* gamma, const float* beta,
+                                         const float* film, int film_ld, int film_off) {
+  const int cpg = C / G;
+  const float inv_cnt = 1.0f / (static_cast<float>(HW) * cpg);
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int l = m.t_lane + j * m.stride;
+    if (l < m.lanes) {
+      float rs[4], nm[4], ga[4], be[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = 4 * l + e;
+        const int g = c / cpg;
+        const float su = __ldg(sums + (static_cast<long long>(n) * G + g) * 2);
+        const float sq = __ldg(sums + (static_cast<long long>(n) * G + g) * 2 + 1);
+        const float mean = su * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float r = rsqrtf(var + GN_EPS);
+        rs[e] = r;
+        nm[e] = -mean * r;
+        float gm = __ldg(gamma + c), bt = __ldg(beta + c);
+        if (film != nullptr) {
+          const float ta = __ldg(film + static_cast<long long>(n) * film_ld + film_off + c);
+          const float tb = __ldg(film + static_cast<long long>(n) * film_ld + film_off + C + c);
+          gm = gm * (1.f + ta);
+          bt = bt * (1.f + ta) + tb;
+        }
+        ga[e] = gm;
+        be[e] = bt;
+      }
+      k.rs[j] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+      k.nm[j] = make_float4(nm[0], nm[1], nm[2], nm[3]);
+      k.ga[j] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+      k.be[j] = make_float4(be[0], be[1], be[2], be[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ film, int film_ld, int film_off,
+                int silu, __half* __restrict__ y16, __half* __restrict__ raw16) {
+  const int C = x.c0 + x.c1;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(HW, gridDim.x));
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  if (!m.active) return;
+  GnCoef k;
+  gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
+    const long long pix = static_cast<long long>(n) * HW + p;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        const float4 v = ld_src(x, pix, 4 * l);
+        float u0 = (v.x * k.rs[j].x + k.nm[j].x) * k.ga[j].x + k.be[j].x;
+        float u1 = (v.y * k.rs[j].y + k.nm[j].y) * k.ga[j].y + k.be[j].y;
+        float u2 = (v.z * k.rs[j].z + k.nm[j].z) * k.ga[j].z + k.be[j].z;
+        float u3 = (v.w * k.rs[j].w + k.nm[j].w) * k.ga[j].w + k.be[j].w;
+        if (silu) {
+          u0 = siluf_(u0); u1 = siluf_(u1); u2 = siluf_(u2); u3 = siluf_(u3);
+        }
+        st_half4(y16 + pix * C + 4 * l, u0, u1, u2, u3);
+        if (raw16 != nullptr) st_half4(raw16 + pix * C + 4 * l, v.x, v.y, v.z, v.w);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+gn_bwd_reduce_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ film, int film_ld, int film_off, int silu,
+                     float* __restrict__ ab) {
+  const int C = x.c0 + x.c1;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(HW, gridDim.x));
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  if (!m.active) return;
+  GnCoef k;
+  gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  float4 A[NL], Bq[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    A[j] = make_float4(0, 0, 0, 0);
+    Bq[j] = make_float4(0, 0, 0, 0);
+  }
+  for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
+    const long long pix = static_cast<long long>(n) * HW + p;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        const float4 v = ld_src(x, pix, 4 * l);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + pix * C + 4 * l));
+        const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
+                             v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
+        const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
+        const float be[4] = {k.be[j].x, k.be[j].y, k.be[j].z, k.be[j].w};
+        float du[4] = {d.x, d.y, d.z, d.w};
+        if (silu) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) du[e] *= silu_grad(xh[e] * ga[e] + be[e]);
+        }
+        A[j].x += du[0]; A[j].y += du[1]; A[j].z += du[2]; A[j].w += du[3];
+        Bq[j].x += du[0] * xh[0]; Bq[j].y += du[1] * xh[1]; Bq[j].z += du[2] * xh[2]; Bq[j].w += du[3] * xh[3];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int l = m.t_lane + j * m.stride;
+    if (l < m.lanes) {
+      float* o = ab + (static_cast<long long>(n) * C + 4 * l) * 2;
+      atomicAdd(o + 0, A[j].x); atomicAdd(o + 1, Bq[j].x);
+      atomicAdd(o + 2, A[j].y); atomicAdd(o + 3, Bq[j].y);
+      atomicAdd(o + 4, A[j].z); atomicAdd(o + 5, Bq[j].z);
+      atomicAdd(o + 6, A[j].w); atomicAdd(o + 7, Bq[j].w);
+    }
+  }
+}
+
+__global__ void gn_bwd_finalize_kernel(int C, int G, int HW, const float* __restrict__ ab,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ film, int film_ld, int film_off,
+                                       float* __restrict__ pg, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ dfilm,
+                                       const float* __restrict__ inv_scale) {
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  __shared__ float p1[128], p2[128];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    p1[i] = 0.f;
+    p2[i] = 0.f;
+  }
+  __syncthreads();
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float A = ab[(static_cast<long long>(n) * C + c) * 2];
+    const float B = ab[(static_cast<long long>(n) * C + c) * 2 + 1];
+    const float gm = gamma[c], bt = beta[c];
+    float f = 1.f;
+    if (film != nullptr) {
+      f = 1.f + film[static_cast<long long>(n) * film_ld + film_off + c];
+      if (dfilm != nullptr) {
+        dfilm[static_cast<long long>(n) * 2 * C + c] = gm * B + bt * A;
+        dfilm[static_cast<long long>(n) * 2 * C + C + c] = A;
+      }
+    }
+    atomicAdd(&p1[c / cpg], gm * f * A);
+    atomicAdd(&p2[c / cpg], gm * f * B);
+    atomicAdd(&dgamma[c], inv * f * B);
+    atomicAdd(&dbeta[c], inv * f * A);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    pg[(static_cast<long long>(n) * G + g) * 2 + 0] = p1[g];
+    pg[(static_cast<long long>(n) * G + g) * 2 + 1] = p2[g];
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ film, int film_ld, int film_off, int silu,
+                    const float* __restrict__ pg, const float* __restrict__ extra, Dst2 dst) {
+  const int C = x.c0 + x.c1;
+  const int cpg = C / G;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(HW, gridDim.x));
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  if (!m.active) return;
+  GnCoef k;
+  gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  // per-channel group terms P1/m, P2/m and gamma' (already includes 1+ta)
+  float4 q1[NL], q2[NL];
+  const float inv_m = 1.0f / (static_cast<float>(HW) * cpg);
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int l = m.t_lane + j * m.stride;
+    if (l < m.lanes) {
+      float a[4], b[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int g = (4 * l + e) / cpg;
+        a[e] = __ldg(pg + (static_cast<long long>(n) * G + g) * 2) * inv_m;
+        b[e] = __ldg(pg + (static_cast<long long>(n) * G + g) * 2 + 1) * inv_m;
+      }
+      q1[j] = make_float4(a[0], a[1], a[2], a[3]);
+      q2[j] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+  }
+  for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
+    const long long pix = static_cast<long long>(n) * HW + p;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        const int c = 4 * l;
+        const float4 v = ld_src(x, pix, c);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + pix * C + c));
+        const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
+                             v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
+        const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
+        const float be[4] = {k.be[j].x, k.be[j].y, k.be[j].z, k.be[j].w};
+        const float rs[4] = {k.rs[j].x, k.rs[j].y, k.rs[j].z, k.rs[j].w};
+        const float a1[4] = {q1[j].x, q1[j].y, q1[j].z, q1[j].w};
+        const float a2[4] = {q2[j].x, q2[j].y, q2[j].z, q2[j].w};
+        float du[4] = {d.x, d.y, d.z, d.w};
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (silu) du[e] *= silu_grad(xh[e] * ga[e] + be[e]);
+          r[e] = rs[e] * (du[e] * ga[e] - a1[e] - xh[e] * a2[e]);
+        }
+        if (extra != nullptr) {
+          const float4 ex = __ldg(reinterpret_cast<const float4*>(extra + pix * C + c));
+          r[0] += ex.x; r[1] += ex.y; r[2] += ex.z; r[3] += ex.w;
+        }
+        float* o;
+        int acc;
+        if (c < dst.c0) {
+          o = dst.p0 + pix * dst.c0 + c;
+          acc = dst.acc0;
+        } else {
+          o = dst.p1 + pix * dst.c1 + (c - dst.c0);
+          acc = dst.acc1;
+        }
+        float4 outv = make_float4(r[0], r[1], r[2], r[3]);
+        if (acc) {
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          outv.x += old.x; outv.y += old.y; outv.z += old.z; outv.w += old.w;
+        }
+        *reinterpret_cast<float4*>(o) = outv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ casts and column sums
+template <bool IN_F16>
+__global__ void __launch_bounds__(TPB)
+cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, long long rows, int C,
+                   float* __restrict__ colsum, const float* __restrict__ inv_scale) {
+  const LaneMap m = lane_map(C);
+  const long long per = cdiv(rows, gridDim.x);
+  const long long r_begin = blockIdx.x * per;
+  const long long r_end = min(rows, r_begin + per);
+  if (!m.active) return;
+  float4 s[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) s[j] = make_float4(0, 0, 0, 0);
+  for (long long r = r_begin + m.sub; r < r_end; r += m.ppi) {
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        float4 v;
+        if (IN_F16) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(in_) + r * C + 4 * l));
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          v = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          v = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in_) + r * C + 4 * l));
+          if (out16 != nullptr) st_half4(out16 + r * C + 4 * l, v.x, v.y, v.z, v.w);
+        }
+        s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
+      }
+    }
+  }
+  if (colsum == nullptr) return;
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int l = m.t_lane + j * m.stride;
+    if (l < m.lanes) {
+      atomicAdd(colsum + 4 * l + 0, inv * s[j].x);
+      atomicAdd(colsum + 4 * l + 1, inv * s[j].y);
+      atomicAdd(colsum + 4 * l + 2, inv * s[j].z);
+      atomicAdd(colsum + 4 * l + 3, inv * s[j].w);
+    }
+  }
+}
+
+__global__ void cast_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + i));
+    st_half4(out + i, v.x, v.y, v.z, v.w);
+  }
+  if (i < n) {
+    for (long long k = i; k < n && k < i + 4; ++k) out[k] = __float2half_rn(in[k]);
+  }
+}
+
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ a,
+                               const float* __restrict__ b, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = a[i] + b[i];
+}
+__global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict__ a, float alpha,
+                                long long n, int acc) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (acc ? dst[i] : 0.f) + alpha * a[i];
+}
+
+// ------------------------------------------------------------------ softmax (warp per row)
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ scores, __half* __restrict__ P16, long long rows, int S, int ld,
+                    const float* __restrict__ mask, long long rows_per_batch) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* s = scores + row * ld;
+  const float* mk = mask != nullptr ? mask + (row / rows_per_batch) * S : nullptr;
+  float mx = -INFINITY;
+  for (int i = lane; i < S; i += 32) {
+    float v = s[i];
+    if (mk != nullptr && mk[i] == 0.f) v = -INFINITY;
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < S; i += 32) {
+    float v = s[i];
+    if (mk != nullptr && mk[i] == 0.f) v = -INFINITY;
+    sum += expf(v - mx);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __half* o = P16 + row * ld;
+  for (int i = lane; i < S; i += 32) {
+    float v = s[i];
+    if (mk != nullptr && mk[i] == 0.f) v = -INFINITY;
+    o[i] = __float2half_rn(expf(v - mx) * inv);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_bwd_rows_kernel(const __half* __restrict__ P16, const float* __restrict__ dP,
+                        __half* __restrict__ dS16, long long rows, int S, int ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __half* p = P16 + row * ld;
+  const float* d = dP + row * ld;
+  float dot = 0.f;
+  for (int i = lane; i < S; i += 32) dot += __half2float(p[i]) * d[i];
+  dot = warp_sum(dot);
+  __half* o = dS16 + row * ld;
+  for (int i = lane; i < S; i += 32) o[i] = __float2half_rn(__half2float(p[i]) * (d[i] - dot) * scale);
+}
+
+// ------------------------------------------------------------------ LayerNorm (block per row)
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (l == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                     __half* __restrict__ y16, float* __restrict__ stats, int D) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s += xr[i];
+  const float mean = block_sum(s, sh) / D;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const float d = xr[i] - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, sh) / D;
+  const float rstd = rsqrtf(var + 1e-5f);
+  if (threadIdx.x == 0) {
+    stats[row * 2] = mean;
+    stats[row * 2 + 1] = rstd;
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x)
+    y16[row * D + i] = __float2half_rn((xr[i] - mean) * rstd * w[i] + b[i]);
+}
+
+constexpr int LN_ROWS = 16;
+constexpr int LN_COLS = 8;  // columns per thread => D <= 256 * 8
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ stats,
+                     const float* __restrict__ dy, float* __restrict__ dx, int acc_dx,
+                     float* __restrict__ dw, float* __restrict__ db, const float* __restrict__ inv_scale,
+                     long long rows, int D) {
+  __shared__ float sh[32];
+  const long long r0 = static_cast<long long>(blockIdx.x) * LN_ROWS;
+  float aw[LN_COLS], abias[LN_COLS], wv[LN_COLS];
+#pragma unroll
+  for (int j = 0; j < LN_COLS; ++j) {
+    aw[j] = 0.f;
+    abias[j] = 0.f;
+    const int i = threadIdx.x + j * 256;
+    wv[j] = i < D ? w[i] : 0.f;
+  }
+  for (int rr = 0; rr < LN_ROWS; ++rr) {
+    const long long row = r0 + rr;
+    if (row >= rows) break;  // uniform across the block
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float xh[LN_COLS], g[LN_COLS];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_COLS; ++j) {
+      const int i = threadIdx.x + j * 256;
+      xh[j] = 0.f;
+      g[j] = 0.f;
+      if (i < D) {
+        xh[j] = (x[row * D + i] - mean) * rstd;
+        const float d = dy[row * D + i];
+        g[j] = d * wv[j];
+        aw[j] += d * xh[j];
+        abias[j] += d;
+        c1 += g[j];
+        c2 += g[j] * xh[j];
+      }
+    }
+    c1 = block_sum(c1, sh) / D;
+    c2 = block_sum(c2, sh) / D;
+#pragma unroll
+    for (int j = 0; j < LN_COLS; ++j) {
+      const int i = threadIdx.x + j * 256;
+      if (i < D) {
+        const float v = rstd * (g[j] - c1 - xh[j] * c2);
+        float* o = dx + row * D + i;
+        *o = acc_dx ? (*o + v) : v;
+      }
+    }
+  }
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+#pragma unroll
+  for (int j = 0; j < LN_COLS; ++j) {
+    const int i = threadIdx.x + j * 256;
+    if (i < D) {
+      atomicAdd(dw + i, inv * aw[j]);
+      atomicAdd(db + i, inv * abias[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ embeddings / activations
+__global__ void sinusoid_embed_kernel(const long long* __restrict__ times, const float* __restrict__ values,
+                                      float const_value, float clamp_default, const float* __restrict__ freq,
+                                      int B, int half, __half* __restrict__ e16) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx - b * half;
+  float v;
+  if (times != nullptr) v = static_cast<float>(times[b]);
+  else if (values != nullptr) v = values[b];
+  else v = const_value;
+  if (clamp_default > 0.f) v = fminf(v / clamp_default, 1.0f) * clamp_default;
+  const float w = freq[i];
+  const float a = v * w;
+  e16[static_cast<long long>(b) * 2 * half + i] = __float2half_rn(sinf(a));
+  e16[static_cast<long long>(b) * 2 * half + half + i] = __float2half_rn(cosf(a));
+}
+
+__global__ void silu_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) y[i] = __float2half_rn(siluf_(x[i]));
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                float* __restrict__ dx, long long n, int acc) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = dy[i] * silu_grad(x[i]);
+    dx[i] = acc ? dx[i] + v : v;
+  }
+}
+__global__ void gelu_bwd_kernel(const __half* __restrict__ u16, const float* __restrict__ dg,
+                                __half* __restrict__ du16, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float u = __half2float(u16[i]);
+    const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * u * u);
+    du16[i] = __float2half_rn(dg[i] * (cdf + u * pdf));
+  }
+}
+
+__global__ void masked_mean_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                   float* __restrict__ y, __half* __restrict__ y16, int S, int D) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f, cnt = 0.f;
+  for (int t = 0; t < S; ++t) {
+    const float mk = mask != nullptr ? mask[static_cast<long long>(b) * S + t] : 1.f;
+    s += mk * x[(static_cast<long long>(b) * S + t) * D + d];
+    cnt += mk;
+  }
+  const float v = s / cnt;
+  y[static_cast<long long>(b) * D + d] = v;
+  if (y16 != nullptr) y16[static_cast<long long>(b) * D + d] = __float2half_rn(v);
+}
+__global__ void masked_mean_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ mask,
+                                       float* __restrict__ dx, int acc, int S, int D) {
+  const int b = blockIdx.z, t = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float cnt = 0.f;
+  for (int i = 0; i < S; ++i) cnt += mask != nullptr ? mask[static_cast<long long>(b) * S + i] : 1.f;
+  const float mk = mask != nullptr ? mask[static_cast<long long>(b) * S + t] : 1.f;
+  const float v = mk * dy[static_cast<long long>(b) * D + d] / cnt;
+  float* o = dx + (static_cast<long long>(b) * S + t) * D + d;
+  *o = acc ? (*o + v) : v;
+}
+
+// ------------------------------------------------------------------ conv helpers
+__global__ void im2col3x3_kernel(const float* __restrict__ x, __half* __restrict__ col, int N, int H, int W,
+                                 int C, int stride, int Ho, int Wo) {
+  const int lanes = C >> 2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * 9 * lanes;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int l = static_cast<int>(i % lanes);
+    long long t = i / lanes;
+    const int tap = static_cast<int>(t % 9);
+    t /= 9;
+    const int wo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const int h = ho * stride + tap / 3 - 1;
+    const int w = wo * stride + tap % 3 - 1;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<long long>(n) * H + h) * W + w) * C + 4 * l));
+    st_half4(col + ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * 9 * C + tap * C + 4 * l, v.x, v.y, v.z, v.w);
+  }
+}
+
+__global__ void col2im3x3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int acc, int N, int H,
+                                 int W, int C, int stride, int Ho, int Wo) {
+  const int lanes = C >> 2;
+  const long long total = static_cast<long long>(N) * H * W * lanes;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int l = static_cast<int>(i % lanes);
+    long long t = i / lanes;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hn = h + 1 - tap / 3, wn = w + 1 - tap % 3;
+      if (hn < 0 || wn < 0 || (hn % stride) != 0 || (wn % stride) != 0) continue;
+      const int ho = hn / stride, wo = wn / stride;
+      if (ho >= Ho || wo >= Wo) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(
+          dcol + ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * 9 * C + tap * C + 4 * l));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = dx + ((static_cast<long long>(n) * H + h) * W + w) * C + 4 * l;
+    if (acc) {
+      const float4 old = *reinterpret_cast<const float4*>(o);
+      s.x += old.x; s.y += old.y; s.z += old.z; s.w += old.w;
+    }
+    *reinterpret_cast<float4*>(o) = s;
+  }
+}
+
+__global__ void im2col_input_kernel(const float* __restrict__ x, const float* __restrict__ inv_std,
+                                    __half* __restrict__ col, int N, int Cin, int H, int W) {
+  const long long total = static_cast<long long>(N) * H * W;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int w = static_cast<int>(i % W);
+    const long long t = i / W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    const float sc = inv_std != nullptr ? inv_std[n] : 1.f;
+    __align__(16) __half v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __float2half_rn(0.f);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      for (int c = 0; c < Cin; ++c)
+        v[tap * Cin + c] = __float2half_rn(sc * x[((static_cast<long long>(n) * Cin + c) * H + hh) * W + ww]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(col + i * 32);
+    const uint4* s = reinterpret_cast<const uint4*>(v);
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
+  }
+}
+
+__global__ void upsample2x_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int N, int H, int W,
+                                      int C) {
+  const int lanes = C >> 2;
+  const long long total = static_cast<long long>(N) * (2 * H) * (2 * W) * lanes;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int l = static_cast<int>(i % lanes);
+    long long t = i / lanes;
+    const int w2 = static_cast<int>(t % (2 * W));
+    t /= (2 * W);
+    const int h2 = static_cast<int>(t % (2 * H));
+    const int n = static_cast<int>(t / (2 * H));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(
+        x + ((static_cast<long long>(n) * H + (h2 >> 1)) * W + (w2 >> 1)) * C + 4 * l));
+    st_half4(y + ((static_cast<long long>(n) * 2 * H + h2) * 2 * W + w2) * C + 4 * l, v.x, v.y, v.z, v.w);
+  }
+}
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int acc, int N,
+                                      int H, int W, int C) {
+  const int lanes = C >> 2;
+  const long long total = static_cast<long long>(N) * H * W * lanes;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int l = static_cast<int>(i % lanes);
+    long long t = i / lanes;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            dy + ((static_cast<long long>(n) * 2 * H + 2 * h + a) * 2 * W + 2 * w + b) * C + 4 * l));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    float* o = dx + ((static_cast<long long>(n) * H + h) * W + w) * C + 4 * l;
+    if (acc) {
+      const float4 old = *reinterpret_cast<const float4*>(o);
+      s.x += old.x; s.y += old.y; s.z += old.z; s.w += old.w;
+    }
+    *reinterpret_cast<float4*>(o) = s;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int ldc, float* __restrict__ y, int N, int C,
+                                    int HW) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int p = static_cast<int>(i % HW);
+    const long long t = i / HW;
+    const int c = static_cast<int>(t % C);
+    const int n = static_cast<int>(t / C);
+    y[i] = x[(static_cast<long long>(n) * HW + p) * ldc + c];
+  }
+}
+__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                        __half* __restrict__ y, int ldo, int N, int C, int HW) {
+  const long long total = static_cast<long long>(N) * HW * ldo;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  const float sc = scale != nullptr ? __ldg(scale) : 1.f;
+  for (; i < total; i += gs) {
+    const int c = static_cast<int>(i % ldo);
+    const long long t = i / ldo;
+    const int p = static_cast<int>(t % HW);
+    const int n = static_cast<int>(t / HW);
+    y[i] = c < C ? __float2half_rn(sc * x[(static_cast<long long>(n) * C + c) * HW + p]) : __float2half_rn(0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sample_inv_std_kernel(const float* __restrict__ x, float* __restrict__ inv_std, long long per) {
+  __shared__ float sh[32];
+  const float* xr = x + static_cast<long long>(blockIdx.x) * per;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) s += xr[i];
+  const float mean = block_sum(s, sh) / static_cast<float>(per);
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const float d = xr[i] - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, sh) / static_cast<float>(per - 1);  // unbiased, torch.std default
+  if (threadIdx.x == 0) inv_std[blockIdx.x] = rsqrtf(var);
+}
+
+// ------------------------------------------------------------------ weight (un)packing
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __half* __restrict__ p, int Co, int Ci, int taps) {
+  const long long total = static_cast<long long>(Co) * Ci;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int ci = static_cast<int>(i % Ci);
+    const long long co = i / Ci;
+    for (int t = 0; t < taps; ++t) p[(co * taps + t) * Ci + ci] = __float2half_rn(w[i * taps + t]);
+  }
+}
+__global__ void pack_conv_in_w_kernel(const float* __restrict__ w, __half* __restrict__ p, int Co, int Ci) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Co * 32) return;
+  const int co = i / 32, k = i % 32;
+  float v = 0.f;
+  if (k < 9 * Ci) {
+    const int tap = k / Ci, c = k % Ci;
+    v = w[(static_cast<long long>(co) * Ci + c) * 9 + tap];
+  }
+  p[i] = __float2half_rn(v);
+}
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci,
+                                         int taps, int ci_ld, const float* __restrict__ inv_scale) {
+  const long long total = static_cast<long long>(Co) * Ci;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+  for (; i < total; i += gs) {
+    const int ci = static_cast<int>(i % Ci);
+    const long long co = i / Ci;
+    for (int t = 0; t < taps; ++t) g[i * taps + t] += inv * packed[(co * taps + t) * ci_ld + ci];
+  }
+}
+__global__ void unpack_conv_in_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co,
+                                            int Ci, const float* __restrict__ inv_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Co * Ci * 9) return;
+  const int tap = i % 9;
+  const int c = (i / 9) % Ci;
+  const int co = i / (9 * Ci);
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+  g[i] += inv * packed[co * 32 + tap * Ci + c];
+}
+
+// ------------------------------------------------------------------ gradient scale
+__global__ void __launch_bounds__(256) grad_amax_kernel(const float* __restrict__ g, long long n,
+                                                        float* __restrict__ amax) {
+  float m = 0.f;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += gs) {
+    const float v = fabsf(g[i]);
+    if (v < INFINITY) m = fmaxf(m, v);  // skips NaN/Inf
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f)
+    atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));  // non-negative floats order as ints
+}
+__global__ void grad_scale_finalize_kernel(const float* __restrict__ amax, float* __restrict__ scale,
+                                           float* __restrict__ inv_scale) {
+  const float a = amax[0];
+  float s = 1.f;
+  if (a > 0.f && a < INFINITY) {
+    int e;
+    frexpf(a, &e);  // a = m * 2^e, m in [0.5, 1)
+    int k = 4 - e;
+    k = max(-100, min(100, k));
+    s = ldexpf(1.f, k);
+  }
+  scale[0] = s;
+  inv_scale[0] = 1.f / s;
+}
+
+inline int grid_for(long long n, int tpb = 256, int cap = 148 * 16) {
+  long long g = cdiv(n, tpb);
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+// ======================================================================== launchers
+void gn_stats(const Src2& x, int N, int HW, int G, float* sums, cudaStream_t st) {
+  const int C = x.c0 + x.c1;
+  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
+  gn_stats_kernel<<<grid, TPB, 0, st>>>(x, HW, G, sums);
+  MDM_LAUNCHED();
+}
+void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const float* gamma, const float* beta,
+              const float* film, int film_ld, int film_off, int silu, __half* y16, __half* raw16,
+              cudaStream_t st) {
+  const int C = x.c0 + x.c1;
+  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
+  gn_apply_kernel<<<grid, TPB, 0, st>>>(x, HW, G, sums, gamma, beta, film, film_ld, film_off, silu, y16, raw16);
+  MDM_LAUNCHED();
+}
+void gn_bwd_reduce(const Src2& x, const float* dy, int N, int HW, int G, const float* sums, const float* gamma,
+                   const float* beta, const float* film, int film_ld, int film_off, int silu, float* ab,
+                   cudaStream_t st) {
+  const int C = x.c0 + x.c1;
+  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
+  gn_bwd_reduce_kernel<<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld, film_off, silu, ab);
+  MDM_LAUNCHED();
+}
+void gn_bwd_finalize(int N, int C, int G, int HW, const float* ab, const float* gamma, const float* beta,
+                     const float* film, int film_ld, int film_off, float* pg, float* dgamma, float* dbeta,
+                     float* dfilm, const float* inv_scale, cudaStream_t st) {
+  gn_bwd_finalize_kernel<<<N, 256, 0, st>>>(C, G, HW, ab, gamma, beta, film, film_ld, film_off, pg, dgamma,
+                                            dbeta, dfilm, inv_scale);
+  MDM_LAUNCHED();
+}
+void gn_bwd_apply(const Src2& x, const float* dy, int N, int HW, int G, const float* sums, const float* gamma,
+                  const float* beta, const float* film, int film_ld, int film_off, int silu, const float* pg,
+                  const float* extra, const Dst2& dst, cudaStream_t st) {
+  const int C = x.c0 + x.c1;
+  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
+  gn_bwd_apply_kernel<<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld, film_off, silu, pg,
+                                            extra, dst);
+  MDM_LAUNCHED();
+}
+
+void cast_colsum(const float* in, __half* out16, long long rows, int C, float* colsum, const float* inv_scale,
+                 cudaStream_t st) {
+  long long chunks = cdiv(rows, host_ppi(C));
+  if (chunks > 148 * 4) chunks = 148 * 4;
+  cast_colsum_kernel<false><<<static_cast<int>(chunks), TPB, 0, st>>>(in, out16, rows, C, colsum, inv_scale);
+  MDM_LAUNCHED();
+}
+void colsum_f16(const __half* in, long long rows, int C, float* colsum, const float* inv_scale, cudaStream_t st) {
+  long long chunks = cdiv(rows, host_ppi(C));
+  if (chunks > 148 * 4) chunks = 148 * 4;
+  cast_colsum_kernel<true><<<static_cast<int>(chunks), TPB, 0, st>>>(in, nullptr, rows, C, colsum, inv_scale);
+  MDM_LAUNCHED();
+}
+void cast_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st) {
+  cast_f32_to_f16_kernel<<<grid_for(cdiv(n, 4)), 256, 0, st>>>(in, out, n);
+  MDM_LAUNCHED();
+}
+void add_f32(float* dst, const float* a, const float* b, long long n, cudaStream_t st) {
+  add_f32_kernel<<<grid_for(n), 256, 0, st>>>(dst, a, b, n);
+  MDM_LAUNCHED();
+}
+void axpy_f32(float* dst, const float* a, float alpha, long long n, int acc, cudaStream_t st) {
+  axpy_f32_kernel<<<grid_for(n), 256, 0, st>>>(dst, a, alpha, n, acc);
+  MDM_LAUNCHED();
+}
+
+void softmax_rows(const float* scores, __half* P16, long long rows, int S, int ld, const float* mask,
+                  long long rows_per_batch, cudaStream_t st) {
+  softmax_rows_kernel<<<static_cast<unsigned>(cdiv(rows, 8)), 256, 0, st>>>(scores, P16, rows, S, ld, mask,
+                                                                          rows_per_batch);
+  MDM_LAUNCHED();
+}
+void softmax_bwd_rows(const __half* P16, const float* dP, __half* dS16, long long rows, int S, int ld, float scale,
+                      cudaStream_t st) {
+  softmax_bwd_rows_kernel<<<static_cast<unsigned>(cdiv(rows, 8)), 256, 0, st>>>(P16, dP, dS16, rows, S, ld, scale);
+  MDM_LAUNCHED();
+}
+
+void layernorm_fwd(const float* x, const float* w, const float* b, __half* y16, float* stats, long long rows, int D,
+                   cudaStream_t st) {
+  layernorm_fwd_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(x, w, b, y16, stats, D);
+  MDM_LAUNCHED();
+}
+void layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, float* dx, int acc_dx,
+                   float* dw, float* db, const float* inv_scale, long long rows, int D, cudaStream_t st) {
+  layernorm_bwd_kernel<<<static_cast<unsigned>(cdiv(rows, LN_ROWS)), 256, 0, st>>>(x, w, stats, dy, dx, acc_dx, dw,
+                                                                                 db, inv_scale, rows, D);
+  MDM_LAUNCHED();
+}
+
+void sinusoid_embed(const long long* times, const float* values, float const_value, float clamp_default,
+                    const float* freq, int B, int half, __half* e16, cudaStream_t st) {
+  sinusoid_embed_kernel<<<static_cast<unsigned>(cdiv(static_cast<long long>(B) * half, 256)), 256, 0, st>>>(
+      times, values, const_value, clamp_default, freq, B, half, e16);
+  MDM_LAUNCHED();
+}
+void silu_f16(const float* x, __half* y16, long long n, cudaStream_t st) {
+  silu_f16_kernel<<<grid_for(n), 256, 0, st>>>(x, y16, n);
+  MDM_LAUNCHED();
+}
+void silu_bwd(const float* x, const float* dy, float* dx, long long n, int acc, cudaStream_t st) {
+  silu_bwd_kernel<<<grid_for(n), 256, 0, st>>>(x, dy, dx, n, acc);
+  MDM_LAUNCHED();
+}
+void gelu_bwd(const __half* u16, const float* dg, __half* du16, long long n, cudaStream_t st) {
+  gelu_bwd_kernel<<<grid_for(n), 256, 0, st>>>(u16, dg, du16, n);
+  MDM_LAUNCHED();
+}
+void masked_mean(const float* x, const float* mask, float* y, __half* y16, int B, int S, int D, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(cdiv(D, 256)), B);
+  masked_mean_kernel<<<grid, 256, 0, st>>>(x, mask, y, y16, S, D);
+  MDM_LAUNCHED();
+}
+void masked_mean_bwd(const float* dy, const float* mask, float* dx, int acc, int B, int S, int D, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(cdiv(D, 256)), S, B);
+  masked_mean_bwd_kernel<<<grid, 256, 0, st>>>(dy, mask, dx, acc, S, D);
+  MDM_LAUNCHED();
+}
+
+void im2col3x3(const float* x, __half* col16, int N, int H, int W, int C, int stride, cudaStream_t st) {
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo * 9 * (C / 4);
+  im2col3x3_kernel<<<grid_for(total), 256, 0, st>>>(x, col16, N, H, W, C, stride, Ho, Wo);
+  MDM_LAUNCHED();
+}
+void col2im3x3(const float* dcol, float* dx, int acc, int N, int H, int W, int C, int stride, cudaStream_t st) {
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = static_cast<long long>(N) * H * W * (C / 4);
+  col2im3x3_kernel<<<grid_for(total), 256, 0, st>>>(dcol, dx, acc, N, H, W, C, stride, Ho, Wo);
+  MDM_LAUNCHED();
+}
+void im2col_input(const float* x_nchw, const float* inv_std, __half* col16, int N, int Cin, int H, int W,
+                  cudaStream_t st) {
+  im2col_input_kernel<<<grid_for(static_cast<long long>(N) * H * W, 128), 128, 0, st>>>(x_nchw, inv_std, col16, N,
+                                                                                      Cin, H, W);
+  MDM_LAUNCHED();
+}
+void upsample2x_f16(const float* x, __half* y16, int N, int H, int W, int C, cudaStream_t st) {
+  upsample2x_f16_kernel<<<grid_for(static_cast<long long>(N) * 4 * H * W * (C / 4)), 256, 0, st>>>(x, y16, N, H, W, C);
+  MDM_LAUNCHED();
+}
+void upsample2x_bwd(const float* dy, float* dx, int acc, int N, int H, int W, int C, cudaStream_t st) {
+  upsample2x_bwd_kernel<<<grid_for(static_cast<long long>(N) * H * W * (C / 4)), 256, 0, st>>>(dy, dx, acc, N, H, W, C);
+  MDM_LAUNCHED();
+}
+void nhwc_to_nchw(const float* x, int ldc, float* y, int N, int C, int HW, cudaStream_t st) {
+  nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * C * HW), 256, 0, st>>>(x, ldc, y, N, C, HW);
+  MDM_LAUNCHED();
+}
+void nchw_to_nhwc_f16(const float* x_nchw, const float* scale, __half* y16, int ldo, int N, int C, int HW,
+                      cudaStream_t st) {
+  nchw_to_nhwc_f16_kernel<<<grid_for(static_cast<long long>(N) * HW * ldo), 256, 0, st>>>(x_nchw, scale, y16, ldo, N,
+                                                                                         C, HW);
+  MDM_LAUNCHED();
+}
+void sample_inv_std(const float* x, float* inv_std, int N, long long per, cudaStream_t st) {
+  sample_inv_std_kernel<<<N, 256, 0, st>>>(x, inv_std, per);
+  MDM_LAUNCHED();
+}
+
+void pack_conv_w(const float* w_oihw, __half* packed, int Co, int Ci, int taps, cudaStream_t st) {
+  pack_conv_w_kernel<<<grid_for(static_cast<long long>(Co) * Ci), 256, 0, st>>>(w_oihw, packed, Co, Ci, taps);
+  MDM_LAUNCHED();
+}
+void pack_conv_in_w(const float* w_oihw, __half* packed, int Co, int Ci, cudaStream_t st) {
+  pack_conv_in_w_kernel<<<static_cast<unsigned>(cdiv(Co * 32, 256)), 256, 0, st>>>(w_oihw, packed, Co, Ci);
+  MDM_LAUNCHED();
+}
+void unpack_conv_wgrad(const float* packed, float* g_oihw, int Co, int Ci, int taps, int ci_ld,
+                       const float* inv_scale, cudaStream_t st) {
+  unpack_conv_wgrad_kernel<<<grid_for(static_cast<long long>(Co) * Ci), 256, 0, st>>>(packed, g_oihw, Co, Ci, taps,
+                                                                                     ci_ld, inv_scale);
+  MDM_LAUNCHED();
+}
+void unpack_conv_in_wgrad(const float* packed, float* g_oihw, int Co, int Ci, const float* inv_scale,
+                          cudaStream_t st) {
+  unpack_conv_in_wgrad_kernel<<<static_cast<unsigned>(cdiv(Co * Ci * 9, 256)), 256, 0, st>>>(packed, g_oihw, Co, Ci,
+                                                                                           inv_scale);
+  MDM_LAUNCHED();
+}
+
+void grad_amax(const float* g, long long n, float* amax_buf, cudaStream_t st) {
+  grad_amax_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(g, n, amax_buf);
+  MDM_LAUNCHED();
+}
+void grad_scale_finalize(const float* amax_buf, float* scale, float* inv_scale, cudaStream_t st) {
+  grad_scale_finalize_kernel<<<1, 1, 0, st>>>(amax_buf, scale, inv_scale);
+  MDM_LAUNCHED();
+}
+
+}  // namespace mdm
