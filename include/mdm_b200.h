@@ -157,6 +157,38 @@ uint64_t mdm_net_workspace_high_water(const mdm_net* net);
  * Returns its element count, or negative if unknown. Layout NHWC. */
 int64_t mdm_net_debug_fetch(mdm_net* net, const char* name, float* dst, int64_t max_elems, mdm_stream_t stream);
 
+
+/* ---------------------------------------------------------------- diffusion algebra (NCHW fp32) */
+/* gammas: device fp32 table of num_diffusion_steps+1 entries (Sampler.gammas, samplers.py:201-231),
+ * for nested pipelines the per-level shifted table (samplers.py:255-264,613-623).
+ * prediction/loss types use the values of samplers.PredictionType: DDPM=3, DDIM=4, V_PREDICTION=5. */
+
+/* x_t = sqrt(g) * (x / image_div) + sqrt(1-g) * eps with g = gammas[t[b] + t_offset]  (samplers.py:244-246) */
+int mdm_q_sample(const float* x, const float* eps, const int64_t* t, const float* gammas, int t_offset,
+                 float image_div, float* x_t, int batch, int64_t per_sample, mdm_stream_t stream);
+/* loss[b] += weight * mean_chw (pred_for_training - target)^2 with g = gammas[t[b] + 1]
+ * (diffusion.py:123-136,160-168; samplers.py:266-279). loss must be zero-initialised by the caller.
+ * pred_out / tgt_out (optional) receive the converted prediction and the target. */
+int mdm_loss_fwd(const float* model_out, const float* x_t, const float* x, const float* eps, const int64_t* t,
+                 const float* gammas, int prediction_type, int loss_type, float image_div, float weight,
+                 float* loss, float* pred_out, float* tgt_out, int batch, int64_t per_sample, mdm_stream_t stream);
+/* d loss / d model_out given dloss (batch,) */
+int mdm_loss_bwd(const float* model_out, const float* x_t, const float* x, const float* eps, const int64_t* t,
+                 const float* gammas, int prediction_type, int loss_type, float image_div, float weight,
+                 const float* dloss, float* dmodel_out, int batch, int64_t per_sample, mdm_stream_t stream);
+/* Sampler.get_prediction_xt_last (samplers.py:281-345) for one level: g = gammas[t_index],
+ * g_last = gammas[s_index]. use_ddim=0: DDPM posterior mean (ddim_eta is None). x0_out optional. */
+int mdm_sampler_step(const float* x_t, const float* pred, const float* noise, const float* gammas, int t_index,
+                     int s_index, int prediction_type, int clip, float image_scale, int use_ddim, float ddim_eta,
+                     int need_noise, float* x0_out, float* x_s_out, int64_t numel, mdm_stream_t stream);
+/* classifier-free guidance: out = uncond + w * (cond - uncond)  (samplers.py:449-455) */
+int mdm_cfg_combine(const float* uncond, const float* cond, float guidance_scale, float* out, int64_t numel,
+                    mdm_stream_t stream);
+/* F.avg_pool2d(x, ratio) over `planes` = batch*channels images of H x W  (diffusion.py:346) */
+int mdm_avg_pool(const float* x, float* y, int planes, int H, int W, int ratio, mdm_stream_t stream);
+/* y = clip(x * scale, -1, 1) if clip else x * scale  (Sampler._postprocess, samplers.py:580-599) */
+int mdm_clip_scale(const float* x, float scale, int clip, float* y, int64_t numel, mdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

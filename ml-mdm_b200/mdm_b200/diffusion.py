@@ -1,0 +1,245 @@
+"""Pipelines behind the reference's `ml_mdm.diffusion` interface (diffusion.py:53-387):
+
+  Model / NestedModel             wrap the vision model (DDP wraps this object in the reference)
+  Diffusion / NestedDiffusion     get_loss(sample) -> (loss(B,), time, x_t, pred, tgt, weights),
+                                  sample(num_examples, sample, image_side, device, **kwargs)
+
+Noising, the v->eps conversion, the per-sample MSE and its gradient are fused CUDA kernels
+(mdm_q_sample, mdm_loss_fwd, mdm_loss_bwd, mdm_avg_pool); the denoiser is the native engine.
+torch supplies RNG draws, device tensors and the autograd graph only.
+"""
+import ctypes as C
+import logging
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, samplers
+from .config import DiffusionConfig, NestedDiffusionConfig  # noqa: F401
+from .samplers import _f32c, _ptr, _stream
+
+
+class _LossFn(torch.autograd.Function):
+    """loss(B,) = sum_levels w_l * mean_chw (pred_for_training_l - target_l)^2 and its gradient w.r.t.
+    the model outputs (diffusion.py:160-168, 367-386)."""
+
+    @staticmethod
+    def forward(ctx, spec, time, *tensors):
+        # tensors: per level (model_out, x_t, x, eps)
+        L = len(spec["levels"])
+        B = tensors[0].shape[0]
+        loss = torch.zeros(B, device=tensors[0].device, dtype=torch.float32)
+        preds, tgts = [], []
+        lib = _lib.lib()
+        saved = []
+        for l in range(L):
+            mo, xt, x, eps = (_f32c(t) for t in tensors[4 * l:4 * l + 4])
+            lv = spec["levels"][l]
+            per = mo.numel() // B
+            want = lv["want_outputs"]
+            p = torch.empty_like(mo) if want else None
+            tg = torch.empty_like(mo) if want else None
+            if lv["weight"] != 0.0 or want:
+                _lib.check(lib.mdm_loss_fwd(_ptr(mo), _ptr(xt), _ptr(x), _ptr(eps), _ptr(time), _ptr(lv["table"]),
+                                            spec["ptype"], spec["ltype"], C.c_float(lv["image_div"]),
+                                            C.c_float(lv["weight"]), _ptr(loss), _ptr(p), _ptr(tg), B,
+                                            C.c_int64(per), _stream()), "mdm_loss_fwd")
+            preds.append(p)
+            tgts.append(tg)
+            saved += [mo, xt, x, eps]
+        ctx.spec = spec
+        ctx.time = time
+        ctx.saved = saved
+        outs = [loss] + [t for t in preds + tgts if t is not None]
+        ctx.mark_non_differentiable(*outs[1:])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dloss, *unused):
+        spec, time, saved = ctx.spec, ctx.time, ctx.saved
+        dloss = _f32c(dloss)
+        lib = _lib.lib()
+        grads = []
+        for l, lv in enumerate(spec["levels"]):
+            mo, xt, x, eps = saved[4 * l:4 * l + 4]
+            if lv["weight"] == 0.0:
+                grads += [torch.zeros_like(mo), None, None, None]
+                continue
+            B = mo.shape[0]
+            d = torch.empty_like(mo)
+            _lib.check(lib.mdm_loss_bwd(_ptr(mo), _ptr(xt), _ptr(x), _ptr(eps), _ptr(time), _ptr(lv["table"]),
+                                        spec["ptype"], spec["ltype"], C.c_float(lv["image_div"]),
+                                        C.c_float(lv["weight"]), _ptr(dloss), _ptr(d), B,
+                                        C.c_int64(mo.numel() // B), _stream()), "mdm_loss_bwd")
+            grads += [d, None, None, None]
+        return (None, None) + tuple(grads)
+
+
+class Model(nn.Module):
+    """diffusion.py:53-87. `forward` returns (outputs, variances placeholder)."""
+
+    def __init__(self, vision_model, diffusion_config=None):
+        super().__init__()
+        self.diffusion_config = diffusion_config if diffusion_config is not None else DiffusionConfig()
+        self._output_scale = self.diffusion_config.model_output_scale
+        if self._output_scale != 0:
+            raise NotImplementedError("model_output_scale (tanh output scaling) is 0 in every shipped config")
+        self.vision_model = vision_model
+        self.sampler = None
+
+    def set_sampler(self, sampler):
+        self.sampler = sampler
+
+    def load(self, vision_file: str) -> dict:
+        return self.vision_model.load(vision_file)
+
+    def save(self, vision_file, other_items=None):
+        self.vision_model.save(vision_file, other_items=other_items)
+
+    @property
+    def input_channels(self):
+        return self.vision_model.input_channels
+
+    def forward(self, x_t, times, lm_outputs, lm_mask, micros={}):
+        outputs = self.vision_model(x_t, times, lm_outputs, lm_mask, micros)
+        # the reference allocates ones_like(outputs) here; a broadcast view keeps the interface
+        return outputs, outputs.new_ones(()).expand_as(outputs)
+
+
+class NestedModel(Model):
+    """diffusion.py:251-292 with no_use_residual=True (the only working mode of the reference)."""
+
+    def forward(self, x_t: List[torch.Tensor], times, lm_outputs, lm_mask, micros={}, mixed_ratio=None):
+        if mixed_ratio is not None:
+            raise NotImplementedError("mixed_ratio batches (partial high-resolution batches) are not built yet")
+        if not self.diffusion_config.no_use_residual:
+            raise NotImplementedError("NestedModel residual mode references an undefined variable in the reference "
+                                      "(diffusion.py:288); shipped configs set no_use_residual: true")
+        return self.vision_model(x_t, times, lm_outputs, lm_mask, micros)
+
+
+class Diffusion(nn.Module):
+    def __init__(self, denoising_model, diffusion_config):
+        super().__init__()
+        logging.info(f"Diffusion config: {diffusion_config}")
+        self.model = Model(denoising_model, diffusion_config)
+        self.sampler = samplers.Sampler(diffusion_config.sampler_config)
+        self.model.set_sampler(self.sampler)
+        self._config = diffusion_config
+
+    def get_model(self):
+        return self.model.module if hasattr(self.model, "module") else self.model
+
+    def to(self, device):
+        self.model = self.model.to(device)
+        self.sampler = self.sampler.to(device)
+        return self
+
+    def train(self, mode: bool = True):
+        self.model.train(mode)
+        return self
+
+    def eval(self):
+        self.model.eval()
+        self.sampler.eval()
+        return self
+
+    def get_micro_conditioning(self, sample: dict) -> dict:
+        micros, conditions = {}, self.get_model().vision_model.conditions
+        if conditions is not None:
+            micros = {key: sample[key] for key in conditions if key in sample}
+        return micros
+
+    def _types(self):
+        sc = self._config.sampler_config
+        return int(sc.prediction_type.value), int(sc.loss_target_type.value)
+
+    def get_loss(self, sample: dict):
+        """diffusion.py:144-168."""
+        images, lm_outputs, lm_mask = sample["images"], sample["lm_outputs"], sample["lm_mask"]
+        sc = self._config.sampler_config
+        eps, time, weights = self.sampler.get_eps_time(images)
+        if not self._config.use_vdm_loss_weights:
+            weights = None
+        rs = sc.rescale_signal
+        x_t = self.sampler.q_sample(images, eps, time, scale=1.0, image_div=float(rs) if rs else 1.0)
+        micros = self.get_micro_conditioning(sample)
+        means, _ = self.model(x_t, time, lm_outputs, lm_mask, micros)
+        ptype, ltype = self._types()
+        spec = dict(ptype=ptype, ltype=ltype,
+                    levels=[dict(table=self.sampler.level_table(1.0, images.device), image_div=1.0, weight=1.0,
+                                 want_outputs=True)])
+        loss, pred, tgt = _LossFn.apply(spec, time, means, x_t, _f32c(images), eps)
+        return loss, time, x_t, means, tgt, weights
+
+    def get_noise(self, num_examples, input_channels, image_side, device):
+        return torch.randn(num_examples, input_channels, image_side, image_side).to(device)
+
+    def sample(self, num_examples: int, sample: dict, image_side: int, device, **kwargs):
+        """diffusion.py:181-197 (noise is drawn on the CPU generator and copied, as in the reference)."""
+        self.eval()
+        noise = self.get_noise(num_examples, self.get_model().input_channels, image_side, device)
+        lm_outputs, lm_mask = sample["lm_outputs"], sample["lm_mask"]
+        micros = self.get_micro_conditioning(sample)
+        return self.sampler.sample(self.get_model(), noise, lm_outputs, lm_mask, micros, **kwargs)
+
+
+class NestedDiffusion(Diffusion):
+    def __init__(self, denoising_model, diffusion_config):
+        nn.Module.__init__(self)
+        logging.info(f"Diffusion config: {diffusion_config}")
+        self.model = NestedModel(denoising_model, diffusion_config)
+        self.sampler = samplers.NestedSampler(diffusion_config.sampler_config)
+        self.model.set_sampler(self.sampler)
+        self._config = diffusion_config
+        self.mixed_ratio = None
+        if getattr(self._config, "mixed_ratio", None):
+            raise NotImplementedError("mixed_ratio batches are not built yet (SURVEY.md 8f rank 4)")
+
+    @staticmethod
+    def avg_pool(x, r):
+        x = _f32c(x)
+        b, c, h, w = x.shape
+        y = torch.empty(b, c, h // r, w // r, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mdm_avg_pool(_ptr(x), _ptr(y), b * c, h, w, int(r), _stream()), "mdm_avg_pool")
+        return y
+
+    def get_loss(self, sample: dict):
+        """diffusion.py:315-387: image pyramid by average pooling, fresh low-resolution noise,
+        per-level shifted schedule, weighted sum of per-level MSE."""
+        images, lm_outputs, lm_mask = sample["images"], sample["lm_outputs"], sample["lm_mask"]
+        micros = self.get_micro_conditioning(sample)
+        vm = self.get_model().vision_model
+        scales = vm.nest_ratio + [1]
+        ratios = [scales[0] // s for s in scales]
+        if any(vm.is_temporal):
+            raise NotImplementedError("temporal mode")
+        eps0, time, weights = self.sampler.get_eps_time(images)
+        if not self._config.use_vdm_loss_weights:
+            weights = None
+        imgs, epss = [_f32c(images)], [eps0]
+        for iz in range(1, len(ratios)):
+            rr = ratios[iz] // ratios[iz - 1]
+            imgs.append(self.avg_pool(imgs[-1], rr))
+        for iz in range(1, len(ratios)):
+            epss.append(torch.empty_like(imgs[iz]).normal_())
+        x_t = [self.sampler.q_sample(x, e, time, scale=s, image_div=self.sampler.level_image_div(s))
+               for x, e, s in zip(imgs, epss, scales)]
+        p_t = self.model(x_t, time, lm_outputs, lm_mask, micros, self.mixed_ratio)
+        if self._config.multi_res_weights is not None:
+            assert self._config.use_double_loss, "only makes sense when applying more losses"
+            w = [float(v) for v in self._config.multi_res_weights.split(":")]
+        else:
+            w = [1.0] * len(x_t)
+        ptype, ltype = self._types()
+        levels, flat = [], []
+        for i, (p, xt, x, e, s) in enumerate(zip(p_t, x_t, imgs, epss, scales)):
+            active = (i == 0) or self._config.use_double_loss
+            levels.append(dict(table=self.sampler.level_table(s, images.device),
+                               image_div=self.sampler.level_image_div(s), weight=w[i] if active else 0.0,
+                               want_outputs=(i == 0)))
+            flat += [p, xt, x, e]
+        loss, pred0, tgt0 = _LossFn.apply(dict(ptype=ptype, ltype=ltype, levels=levels), time, *flat)
+        return loss, time, x_t[0], pred0, tgt0, weights
