@@ -17,5 +17,5 @@ done
 for p in "${pids[@]}"; do wait $p; done
 OBJS=""
 for f in gemm_tc kernels engine net capi diffusion; do [ -f build/$f.o ] && OBJS="$OBJS build/$f.o"; done
-nvcc -shared -o $OUT $OBJS -lcudart
+nvcc -arch=sm_100a -shared -o $OUT $OBJS -lcudart
 echo "built $OUT"

@@ -72,6 +72,11 @@ typedef struct mdm_gemm_params {
   int32_t atomic;
 } mdm_gemm_params;
 
+/* Measurement aid for bench.py's roofline leg: while enabled every launch of the tcgen05 GEMM kernel
+ * is bracketed by CUDA events on its stream; mdm_profile_read returns and clears their sum. */
+int mdm_profile_gemm(int enable);
+int mdm_profile_read(double* total_ms, long long* launches);
+
 int mdm_gemm_raw(const mdm_tmap_spec* A, const mdm_tmap_spec* B, int a_mn, int b_mn,
                  const mdm_gemm_params* p, mdm_stream_t stream);
 

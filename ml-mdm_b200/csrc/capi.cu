@@ -26,6 +26,30 @@ const char* mdm_last_error(void) { return mdm::g_err.c_str(); }
 int mdm_version(void) { return 100; }
 unsigned long long mdm_launch_count(void) { return mdm::g_launch_count; }
 
+int mdm_profile_gemm(int enable) {
+  mdm::g_profile = enable != 0;
+  return 0;
+}
+
+int mdm_profile_read(double* total_ms, long long* launches) {
+  double tot = 0.0;
+  long long n = 0;
+  for (auto& ev : mdm::g_profile_events) {
+    cudaEventSynchronize(ev.second);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  mdm::g_profile_events.clear();
+  *total_ms = tot;
+  *launches = n;
+  return 0;
+}
+
 int mdm_gemm_raw(const mdm_tmap_spec* A, const mdm_tmap_spec* B, int a_mn, int b_mn,
                  const mdm_gemm_params* p, mdm_stream_t stream) {
   int rc = mdm::launch_gemm(*A, *B, a_mn, b_mn, *p, static_cast<cudaStream_t>(stream));

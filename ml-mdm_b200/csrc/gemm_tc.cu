@@ -3,11 +3,19 @@
 
 #include <stdio.h>
 
+#include <utility>
+#include <vector>
+
 #include "ptx.cuh"
 
 namespace mdm {
 
 unsigned long long g_launch_count = 0;
+
+// Optional per-launch timing of this kernel (bench.py's roofline leg): CUDA events on the launching
+// stream around every launch while enabled.
+bool g_profile = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
 
 using namespace ptx;
 
@@ -338,7 +346,17 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+  }
   gemm_tc_kernel<A_MN, B_MN><<<grid, 128, smem, stream>>>(tmA, tmB, p);
+  if (g_profile) {
+    cudaEventRecord(e1, stream);
+    g_profile_events.emplace_back(e0, e1);
+  }
   ++g_launch_count;
   return static_cast<int>(cudaGetLastError());
 }

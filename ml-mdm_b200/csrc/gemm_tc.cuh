@@ -17,6 +17,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+#include <vector>
+
 #include "mdm_b200.h"
 
 namespace mdm {
@@ -38,5 +41,7 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
 
 // Counts kernel launches issued by this library (bench.py reports it as gpu_launches).
 extern unsigned long long g_launch_count;
+extern bool g_profile;
+extern std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
 
 }  // namespace mdm

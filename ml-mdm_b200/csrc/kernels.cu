@@ -9,7 +9,7 @@ namespace mdm {
 namespace {
 
 constexpr int TPB = 256;
-constexpr int NL = 6;  // float4 channel lanes per thread (C <= 4 * TPB * NL)
+constexpr int NL_MAX = 6;  // float4 channel lanes per thread (C <= 4 * TPB * NL_MAX)
 constexpr float GN_EPS = 1e-5f;
 
 #define MDM_LAUNCHED() (++g_launch_count)
@@ -62,19 +62,35 @@ __device__ __forceinline__ void st_half4(__half* p, float a, float b, float c, f
 }
 
 inline int pixel_chunks(int N, int HW, int ppi_hint) {
-  long long want = cdiv(4 * 148, N);
+  long long want = cdiv(8 * 148, N);
   long long maxc = cdiv(HW, ppi_hint > 0 ? ppi_hint : 1);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   if (want > 65535) want = 65535;
   return static_cast<int>(want);
 }
+#define MDM_DISPATCH_NL(C, ...)                    \
+  do {                                            \
+    const int lanes__ = (C) / 4;                  \
+    if (lanes__ <= TPB) {                         \
+      constexpr int NL = 1;                       \
+      __VA_ARGS__;                                \
+    } else if (lanes__ <= 2 * TPB) {              \
+      constexpr int NL = 2;                       \
+      __VA_ARGS__;                                \
+    } else {                                      \
+      constexpr int NL = NL_MAX;                  \
+      __VA_ARGS__;                                \
+    }                                             \
+  } while (0)
+
 inline int host_ppi(int C) {
   int lanes = C / 4;
   return lanes <= TPB ? TPB / lanes : 1;
 }
 
 // ------------------------------------------------------------------ GroupNorm statistics
+template <int NL>
 __global__ void __launch_bounds__(TPB) gn_stats_kernel(Src2 x, int HW, int G, float* __restrict__ sums) {
   const int C = x.c0 + x.c1;
   const int cpg = C / G;
@@ -134,10 +150,12 @@ __global__ void __launch_bounds__(TPB) gn_stats_kernel(Src2 x, int HW, int G, fl
 
 // Per-thread GroupNorm coefficients of its channel lanes: xhat = x*rs + (-mean*rs); u = xhat*ga + be
 // with ga = gamma*(1+ta), be = beta*(1+ta)+tb.
+template <int NL>
 struct GnCoef {
   float4 rs[NL], nm[NL], ga[NL], be[NL];
 };
-__device__ __forceinline__ void gn_coefs(GnCoef& k, const LaneMap& m, int n, int C, int G, int HW,
+template <int NL>
+__device__ __forceinline__ void gn_coefs(GnCoef<NL>& k, const LaneMap& m, int n, int C, int G, int HW,
                                          const float* sums, const float* gamma, const float* beta,
                                          const float* film, int film_ld, int film_off) {
   const int cpg = C / G;
@@ -176,6 +194,7 @@ __device__ __forceinline__ void gn_coefs(GnCoef& k, const LaneMap& m, int n, int
   }
 }
 
+template <int NL>
 __global__ void __launch_bounds__(TPB)
 gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ film, int film_ld, int film_off,
@@ -187,7 +206,7 @@ gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const flo
   const int p_begin = blockIdx.x * per;
   const int p_end = min(HW, p_begin + per);
   if (!m.active) return;
-  GnCoef k;
+  GnCoef<NL> k;
   gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
   for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
     const long long pix = static_cast<long long>(n) * HW + p;
@@ -210,6 +229,7 @@ gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const flo
   }
 }
 
+template <int NL>
 __global__ void __launch_bounds__(TPB)
 gn_bwd_reduce_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -222,7 +242,7 @@ gn_bwd_reduce_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const 
   const int p_begin = blockIdx.x * per;
   const int p_end = min(HW, p_begin + per);
   if (!m.active) return;
-  GnCoef k;
+  GnCoef<NL> k;
   gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
   float4 A[NL], Bq[NL];
 #pragma unroll
@@ -304,6 +324,7 @@ __global__ void gn_bwd_finalize_kernel(int C, int G, int HW, const float* __rest
   }
 }
 
+template <int NL>
 __global__ void __launch_bounds__(TPB)
 gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -317,7 +338,7 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
   const int p_begin = blockIdx.x * per;
   const int p_end = min(HW, p_begin + per);
   if (!m.active) return;
-  GnCoef k;
+  GnCoef<NL> k;
   gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
   // per-channel group terms P1/m, P2/m and gamma' (already includes 1+ta)
   float4 q1[NL], q2[NL];
@@ -385,7 +406,7 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
 }
 
 // ------------------------------------------------------------------ casts and column sums
-template <bool IN_F16>
+template <bool IN_F16, int NL>
 __global__ void __launch_bounds__(TPB)
 cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, long long rows, int C,
                    float* __restrict__ colsum, const float* __restrict__ inv_scale) {
@@ -950,7 +971,7 @@ inline int grid_for(long long n, int tpb = 256, int cap = 148 * 16) {
 void gn_stats(const Src2& x, int N, int HW, int G, float* sums, cudaStream_t st) {
   const int C = x.c0 + x.c1;
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  gn_stats_kernel<<<grid, TPB, 0, st>>>(x, HW, G, sums);
+  MDM_DISPATCH_NL(C, (gn_stats_kernel<NL><<<grid, TPB, 0, st>>>(x, HW, G, sums)));
   MDM_LAUNCHED();
 }
 void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const float* gamma, const float* beta,
@@ -958,7 +979,8 @@ void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const floa
               cudaStream_t st) {
   const int C = x.c0 + x.c1;
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  gn_apply_kernel<<<grid, TPB, 0, st>>>(x, HW, G, sums, gamma, beta, film, film_ld, film_off, silu, y16, raw16);
+  MDM_DISPATCH_NL(C, (gn_apply_kernel<NL><<<grid, TPB, 0, st>>>(x, HW, G, sums, gamma, beta, film, film_ld, film_off, silu,
+                                                                y16, raw16)));
   MDM_LAUNCHED();
 }
 void gn_bwd_reduce(const Src2& x, const float* dy, int N, int HW, int G, const float* sums, const float* gamma,
@@ -966,7 +988,8 @@ void gn_bwd_reduce(const Src2& x, const float* dy, int N, int HW, int G, const f
                    cudaStream_t st) {
   const int C = x.c0 + x.c1;
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  gn_bwd_reduce_kernel<<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld, film_off, silu, ab);
+  MDM_DISPATCH_NL(C, (gn_bwd_reduce_kernel<NL><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
+                                                                     film_off, silu, ab)));
   MDM_LAUNCHED();
 }
 void gn_bwd_finalize(int N, int C, int G, int HW, const float* ab, const float* gamma, const float* beta,
@@ -981,22 +1004,24 @@ void gn_bwd_apply(const Src2& x, const float* dy, int N, int HW, int G, const fl
                   const float* extra, const Dst2& dst, cudaStream_t st) {
   const int C = x.c0 + x.c1;
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  gn_bwd_apply_kernel<<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld, film_off, silu, pg,
-                                            extra, dst);
+  MDM_DISPATCH_NL(C, (gn_bwd_apply_kernel<NL><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
+                                                                    film_off, silu, pg, extra, dst)));
   MDM_LAUNCHED();
 }
 
 void cast_colsum(const float* in, __half* out16, long long rows, int C, float* colsum, const float* inv_scale,
                  cudaStream_t st) {
   long long chunks = cdiv(rows, host_ppi(C));
-  if (chunks > 148 * 4) chunks = 148 * 4;
-  cast_colsum_kernel<false><<<static_cast<int>(chunks), TPB, 0, st>>>(in, out16, rows, C, colsum, inv_scale);
+  if (chunks > 148 * 8) chunks = 148 * 8;
+  MDM_DISPATCH_NL(C, (cast_colsum_kernel<false, NL><<<static_cast<int>(chunks), TPB, 0, st>>>(in, out16, rows, C, colsum,
+                                                                                             inv_scale)));
   MDM_LAUNCHED();
 }
 void colsum_f16(const __half* in, long long rows, int C, float* colsum, const float* inv_scale, cudaStream_t st) {
   long long chunks = cdiv(rows, host_ppi(C));
-  if (chunks > 148 * 4) chunks = 148 * 4;
-  cast_colsum_kernel<true><<<static_cast<int>(chunks), TPB, 0, st>>>(in, nullptr, rows, C, colsum, inv_scale);
+  if (chunks > 148 * 8) chunks = 148 * 8;
+  MDM_DISPATCH_NL(C, (cast_colsum_kernel<true, NL><<<static_cast<int>(chunks), TPB, 0, st>>>(in, nullptr, rows, C, colsum,
+                                                                                            inv_scale)));
   MDM_LAUNCHED();
 }
 void cast_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st) {

@@ -255,7 +255,17 @@ def bench_one(M, N, K, iters=20):
     return ms, fl / ms / 1e9, ms_ref, fl / ms_ref / 1e9
 
 
+def ncu_target():
+    """Three launches of the largest 64x64-level conv of the cc12m_64x64 U-Net at batch 64
+    (3x3, 256->256 @ 64x64: M = 262144 pixels, N = 256, K = 2304) for an `ncu --set full` capture."""
+    for _ in range(3):
+        run_conv_fwd(64, 64, 64, 256, 256, 256, bias=True)
+
+
 if __name__ == "__main__":
+    if "--ncu-conv" in sys.argv:
+        ncu_target()
+        sys.exit(0)
     bad = 0
     for name, fn in CASES:
         try:

@@ -1,0 +1,143 @@
+"""Pipelines on B200 vs the oracle / reference goldens: q-sample (bit-exact), get_loss + gradients,
+DDIM / DDPM / CFG reverse steps, 4-step DDIM sampling, for the tiny UNet and the 2-level nest."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import net_cases as nc
+import tiny_configs as tc
+from mdm_b200 import config as mc
+from mdm_b200.diffusion import Diffusion, NestedDiffusion
+from oracle import diffusion_ref as dref
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def pipeline(kind):
+    model, oracle, sd = nc.build(kind)
+    nested = kind == "nested"
+    dcfg = mc.diffusion_config_from_dict(copy.deepcopy(tc.TINY_NESTED_DIFFUSION if nested else tc.TINY_DIFFUSION), nested)
+    pipe = (NestedDiffusion if nested else Diffusion)(model, dcfg).to("cuda")
+    gold = np.load(os.path.join(GOLD, f"tiny_{kind}.npz"))
+    x, t, lm, mask = tc.seeded_inputs(3, 2, 32 if nested else 16, 6, nlevels=2 if nested else 1)
+    return pipe, oracle, sd, gold, x, lm, mask, nested
+
+
+def test_q_sample_matches_to_one_ulp():
+    """Not bit-exact by construction: torch's CPU sqrt kernel is not correctly rounded (differs from
+    IEEE sqrt in ~0.6% of inputs), the device uses IEEE sqrt.rn; everything else is one rounding per op."""
+    pipe, _, _, _, x, _, _, _ = pipeline("unet")
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(4, 3, 16, 16, generator=g) * 2 - 1
+    eps = torch.randn(4, 3, 16, 16, generator=g)
+    time = torch.tensor([0, 1, 500, 999])
+    gam = dref.gammas_f32("DEEPFLOYD", 1000)
+    ref = dref.q_sample(img, eps, gam[time + 1])
+    got = pipe.sampler.q_sample(img.cuda(), eps.cuda(), time.cuda()).cpu()
+    torch.testing.assert_close(got, ref, rtol=2.5e-7, atol=2.5e-7)
+
+
+@pytest.mark.parametrize("kind", ["unet", "nested"])
+def test_get_loss_and_gradients(kind):
+    pipe, oracle, sd, gold, x, lm, mask, nested = pipeline(kind)
+    images = (x[0] if nested else x).clamp(-1, 1)
+    # the product draws time/eps with torch's CUDA generator; parity is on identical noised inputs, so
+    # the draws are replayed into the oracle
+    torch.manual_seed(1234)
+    pipe.train()
+    loss, time, x_t, pred, tgt, w = pipe.get_loss({"images": images.cuda(), "lm_outputs": lm.cuda(), "lm_mask": mask.cuda()})
+    loss.mean().backward()
+    torch.manual_seed(1234)
+    time_r = torch.randint(0, 1000, (2,), device="cuda")
+    eps = [torch.randn_like(images.cuda())]
+    if nested:
+        eps.append(torch.empty(2, 3, 8, 8, device="cuda").normal_())
+    assert torch.equal(time_r, time) and w is None
+    scales = [4, 1] if nested else [1]
+    P = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    gam = dref.gammas_f32("DEEPFLOYD", 1000)
+    oloss, ox_t, _ = dref.training_loss(oracle, P, images.double(), [e.cpu().double() for e in eps], time.cpu(), lm.double(), mask.double(),
+                                        gam, scales, dref.V_PREDICTION, dref.DDPM, shifted=nested, power=1)
+    assert nc.rel(x_t.cpu().double(), ox_t[0]) <= 1e-6
+    oloss.mean().backward()
+    assert nc.rel(loss.detach().cpu().double(), oloss.detach()) <= 5e-3
+    mags = sorted(float(P[k].grad.abs().max()) for k in P)
+    floor = 1e-3 * mags[len(mags) // 2]
+    bad = {}
+    for k, p in pipe.get_model().vision_model.named_parameters():
+        ref = P[k].grad
+        e = float((p.grad.cpu().double() - ref).abs().max() / max(float(ref.abs().max()), floor))
+        if not e <= 3e-2:
+            bad[k] = e
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("kind", ["unet", "nested"])
+def test_reverse_steps_vs_reference_golden(kind):
+    pipe, _, _, gold, x, lm, mask, nested = pipeline(kind)
+    pipe.eval()
+    smp, m = pipe.sampler, pipe.get_model()
+    xc = [xi.cuda() for xi in x] if nested else x.cuda()
+    lmc, mc_ = lm.cuda(), mask.cuda()
+
+    def clone(v):
+        return [a.clone() for a in v] if nested else v.clone()
+
+    with torch.no_grad():
+        x0, xs, _ = smp.get_xt_minus_1(m, 500, clone(xc), lmc, mc_, {}, time_step_last=480, ddim_eta=0.0, return_details=True)
+        for i, (a, b) in enumerate(zip(x0, xs) if nested else [(x0, xs)]):
+            assert nc.rel(a.cpu(), torch.from_numpy(gold[f"ddim_x0_{i}"])) <= 3e-3
+            assert nc.rel(b.cpu(), torch.from_numpy(gold[f"ddim_xs_{i}"])) <= 3e-3
+        lm2 = torch.cat([torch.zeros_like(lmc), lmc])
+        xs = smp.get_xt_minus_1(m, 500, clone(xc), lm2, torch.cat([mc_, mc_]), {}, time_step_last=480, ddim_eta=0.0,
+                                guidance_scale=3.0)
+        for i, b in enumerate(xs if nested else [xs]):
+            assert nc.rel(b.cpu(), torch.from_numpy(gold[f"cfg_xs_{i}"])) <= 5e-3
+        # stochastic DDPM step: noise comes from the CUDA generator, so compare against the oracle's
+        # deterministic part (posterior mean) by replaying the same noise
+        torch.manual_seed(99)
+        xs = smp.get_xt_minus_1(m, 500, clone(xc), lmc, mc_, {}, time_step_last=499, ddim_eta=None)
+        torch.manual_seed(99)
+        lv = xs if nested else [xs]
+        noises = [torch.randn_like(a) for a in lv]
+        gam = dref.gammas_f32("DEEPFLOYD", 1000)
+        scales = [4, 1] if nested else [1]
+        times = torch.full((2,), 499, dtype=torch.long, device="cuda")
+        preds = m(xc, times, lmc, mc_, {})
+        preds = list(preds) if nested else [preds[0]]
+        for xi, p, s, nz, got in zip(x if nested else [x], preds, scales, noises, lv):
+            tab = dref.shift_table(gam, s, 1) if nested else gam
+            _, ref = dref.reverse_step(xi, p.cpu(), tab[500], tab[499], dref.V_PREDICTION, True, 1.0, None, True, noise=nz.cpu())
+            assert nc.rel(got.cpu(), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("kind", ["unet", "nested"])
+def test_ddim_sampling_vs_reference_golden(kind):
+    pipe, _, _, gold, x, lm, mask, nested = pipeline(kind)
+    pipe.eval()
+    smp, m = pipe.sampler, pipe.get_model()
+    if nested:
+        torch.manual_seed(7)
+        low = torch.empty(2, 3, 8, 8).normal_()  # the golden's low-resolution start (CPU generator)
+        init = [x[0].cuda(), low.cuda()]
+    else:
+        init = x.cuda()
+    out = smp.sample(m, init, lm.cuda(), mask.cuda(), {}, num_inference_steps=4, ddim_eta=0.0, resample_steps=True)
+    assert nc.rel(out.cpu(), torch.from_numpy(gold["sample4"])) <= 1e-2  # 4 network evaluations compound
+    assert float(out.abs().max()) <= 1.0
+
+
+def test_pipeline_sample_entry_point_shapes():
+    pipe, _, _, _, x, lm, mask, _ = pipeline("nested")
+    torch.manual_seed(0)
+    out = pipe.sample(2, {"lm_outputs": lm.cuda(), "lm_mask": mask.cuda()}, 32, torch.device("cuda"),
+                      num_inference_steps=3, ddim_eta=0.0, resample_steps=True)
+    assert out.shape == (2, 3, 32, 32) and bool(torch.isfinite(out).all())
+    gen = pipe.sample(2, {"lm_outputs": lm.cuda(), "lm_mask": mask.cuda()}, 32, torch.device("cuda"),
+                      num_inference_steps=3, ddim_eta=1.0, resample_steps=True, yield_output=True, output_inner=True)
+    frames = list(gen)
+    assert len(frames) == 4 and frames[-1].shape == (2, 3, 32, 64)
