@@ -70,12 +70,15 @@ typedef struct mdm_gemm_params {
   int64_t ldc, c_z1_stride, c_z2_stride;
   int32_t act;
   int32_t atomic;
+  int32_t epi_tma; /* filled by the launcher: staged shared-memory + TMA-store epilogue in use */
 } mdm_gemm_params;
 
 /* Measurement aid for bench.py's roofline leg: while enabled every launch of the tcgen05 GEMM kernel
  * is bracketed by CUDA events on its stream; mdm_profile_read returns and clears their sum. */
 int mdm_profile_gemm(int enable);
 int mdm_profile_read(double* total_ms, long long* launches);
+/* Writes one CSV row per profiled launch (shape, grid parameters, milliseconds); call before mdm_profile_read. */
+int mdm_profile_dump(const char* path);
 
 int mdm_gemm_raw(const mdm_tmap_spec* A, const mdm_tmap_spec* B, int a_mn, int b_mn,
                  const mdm_gemm_params* p, mdm_stream_t stream);

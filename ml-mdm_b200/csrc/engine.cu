@@ -183,7 +183,8 @@ void Engine::gemm_tn(const __half* At, long long lda, const __half* Bm, long lon
   p.kind = GEMM_PLAIN;
   p.M = M; p.N = N; p.K = K;
   const long long mt = (M + 127) / 128;
-  p.block_n = pick_block_n(mt, N, 1);
+  // weight gradients: long contraction, small output -> widest tile, parallelism from split-K
+  p.block_n = e.atomic_ok ? (N >= 256 ? 256 : round16(N)) : pick_block_n(mt, N, 1);
   p.nz1 = p.nz2 = 1;
   p.num_kblocks = (K + 63) / 64;
   fill_epi(p, e, N);
@@ -248,7 +249,7 @@ void Engine::conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int l
   p.M = Cout; p.N = Cin;
   conv_geom(p, N, H, W, 64);
   const long long mt = (Cout + 127) / 128;
-  p.block_n = pick_block_n(mt, Cin, 9);
+  p.block_n = Cin >= 256 ? 256 : round16(Cin);
   p.nz1 = 9;
   p.nz2 = 1;
   p.taps = 9;

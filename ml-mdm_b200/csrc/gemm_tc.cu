@@ -2,6 +2,7 @@
 #include "gemm_tc.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <utility>
 #include <vector>
@@ -16,6 +17,8 @@ unsigned long long g_launch_count = 0;
 // stream around every launch while enabled.
 bool g_profile = false;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
+std::vector<GemmParams> g_profile_params;  // parallel to g_profile_events
+std::vector<int> g_profile_majors;
 
 using namespace ptx;
 
@@ -28,19 +31,33 @@ constexpr int SLAB_BYTES = 64 * 64 * 2;  // one 64(k) x 64(mn) MN-major slab
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_BUDGET = 99 * 1024;  // two CTAs per SM: one runs its epilogue under the other's mainloop
 
+// Exact-erf GELU (nn.GELU() default, unet.py:270) with erf from Abramowitz-Stegun 7.1.26
+// (|abs error| <= 1.5e-7, far below the fp16 rounding of the stored result); one ex2 + one rcp.
 __device__ __forceinline__ float gelu_erf(float v) {
-  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-x * x);
+  const float erf_v = copysignf(erf_abs, v);
+  return 0.5f * v * (1.0f + erf_v);
 }
 
+constexpr int NUM_THREADS = 256;  // warps 0-3: TMA / MMA / epilogue, warps 4-7: epilogue only
+
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NUM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
+               const __grid_constant__ CUtensorMap tmOact, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_bias[256];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -88,6 +105,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(p.block_n)) tmem_cols <<= 1;
   if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+  for (int i = threadIdx.x; i < p.block_n; i += blockDim.x)
+    s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -186,7 +205,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
   }
-  const int r = threadIdx.x;  // TMEM lane == tile row
+  const int r = threadIdx.x & 127;  // TMEM lane == tile row; warps w and w+4 share a lane quarter
+  const int half_id = threadIdx.x >> 7;  // which half of the columns this thread drains
   bool valid;
   long long row_off;
   if (p.kind == GEMM_CONV) {
@@ -204,9 +224,111 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   float alpha = p.alpha;
   if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev);
-  const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
-  for (int c = 0; c < p.block_n; c += 16) {
+  if (p.epi_tma) {
+    // ---- staged epilogue: registers -> 128B-swizzled smem tiles (the freed pipeline stages) -> TMA
+    // stores. Rows/columns outside the tensor are clipped by the TMA unit.
+    uint8_t* st32 = smem;  // 2 x [128][32] fp32
+    uint8_t* st16 = smem + (p.out_f32 != nullptr ? 32768 : 0);
+    uint8_t* stact = st16 + (p.out_f16 != nullptr ? 16384 : 0);
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    const int ngroups = (p.block_n + 63) / 64;
+    int oc1, oc2, oc3;  // output coordinates of the tile origin beyond the column
+    if (p.kind == GEMM_CONV) {
+      oc1 = tw * p.PW;
+      oc2 = th * p.PH;
+      oc3 = img;
+    } else {
+      oc1 = m0;
+      oc2 = z1;
+      oc3 = z2;
+    }
+    for (int g = 0; g < ngroups; ++g) {
+      if (g > 0) {
+        if (threadIdx.x == 0) bulk_wait_read();
+        __syncthreads();
+      }
+#pragma unroll 1
+      for (int ci = 0; ci < 2; ++ci) {
+        const int cc = half_id * 2 + ci;
+        const int c = g * 64 + cc * 16;
+        if (c >= p.block_n) break;  // warp-uniform
+        float v[16];
+        tmem_ld16(taddr_row + static_cast<uint32_t>(c), v);
+        const int col0 = n0 + c;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] * alpha + s_bias[c + j];
+        if (p.residual != nullptr && valid && col0 < p.N) {
+          const long long off0 = row_off + col0;
+          if (col0 + 16 <= p.N && ((off0 & 3) == 0)) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + off0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = __ldg(rp + q);
+              v[4 * q + 0] += t.x;
+              v[4 * q + 1] += t.y;
+              v[4 * q + 2] += t.z;
+              v[4 * q + 3] += t.w;
+            }
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.residual + off0 + j);
+          }
+        }
+        if (p.out_f32 != nullptr) {
+          uint8_t* base = st32 + (cc >> 1) * 16384 + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + q) ^ swz;
+            *reinterpret_cast<float4*>(base + chunk * 16) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+        if (p.out_f16 != nullptr) {
+          uint8_t* base = st16 + r * 128;
+          __half2 h[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[0]);
+          *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[4]);
+        }
+        if (p.out_act_f16 != nullptr) {
+          uint8_t* base = stact + r * 128;
+          __half2 h[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float a0 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q]) : v[2 * q];
+            const float a1 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q + 1]) : v[2 * q + 1];
+            h[q] = __floats2half2_rn(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[0]);
+          *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[4]);
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int colg = n0 + g * 64;
+        if (colg < p.N) {
+          if (p.out_f32 != nullptr) {
+            tma_store_4d(&tmO32, st32, colg, oc1, oc2, oc3);
+            if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_store_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+          }
+          if (p.out_f16 != nullptr) tma_store_4d(&tmO16, st16, colg, oc1, oc2, oc3);
+          if (p.out_act_f16 != nullptr) tma_store_4d(&tmOact, stact, colg, oc1, oc2, oc3);
+        }
+        bulk_commit();
+      }
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
+
+  for (int c = 0; c < p.block_n && half_id == 0; c += 16) {
     float v[16];
     if (nkb > 0) {
       tmem_ld16(taddr_row + static_cast<uint32_t>(c), v);
@@ -221,8 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float x = v[j] * alpha;
-      if (p.bias != nullptr && (full || col0 + j < p.N)) x += __ldg(p.bias + col0 + j);
-      v[j] = x;
+      v[j] = x + s_bias[c + j];
     }
     if (p.residual != nullptr) {
       if (full && ((off0 & 3) == 0)) {
@@ -309,7 +430,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap(CUtensorMap* out, const TmapSpec& s) {
+int encode_tmap(CUtensorMap* out, const TmapSpec& s, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return -1;
   cuuint64_t gdim[4], gstr[3];
@@ -318,8 +439,8 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s) {
     gdim[i] = s.dims[i];
     box[i] = s.box[i];
   }
-  for (int i = 0; i < 3; ++i) gstr[i] = s.strides[i + 1] * 2;  // bytes (fp16)
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.ptr), gdim, gstr, box,
+  for (int i = 0; i < 3; ++i) gstr[i] = s.strides[i + 1] * (f32 ? 4 : 2);  // bytes
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.ptr), gdim, gstr, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -337,7 +458,7 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s) {
 }
 
 template <bool A_MN, bool B_MN>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid,
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const GemmParams& p, dim3 grid,
                 size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -352,10 +473,12 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     cudaEventCreate(&e1);
     cudaEventRecord(e0, stream);
   }
-  gemm_tc_kernel<A_MN, B_MN><<<grid, 128, smem, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<A_MN, B_MN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], p);
   if (g_profile) {
     cudaEventRecord(e1, stream);
     g_profile_events.emplace_back(e0, e1);
+    g_profile_params.push_back(p);
+    g_profile_majors.push_back((A_MN ? 2 : 0) | (B_MN ? 1 : 0));
   }
   ++g_launch_count;
   return static_cast<int>(cudaGetLastError());
@@ -389,7 +512,7 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   if (stages > per) stages = per;
   if (stages < 1) return -13;
   p.num_stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
 
   int m_tiles;
   if (p.kind == GEMM_CONV) {
@@ -401,10 +524,58 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   dim3 grid(m_tiles, n_tiles, p.nz1 * p.nz2 * p.nsplit);
   if (grid.y > 65535 || grid.z > 65535) return -14;
 
-  if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, p, grid, smem, stream);
-  if (!a_mn && b_mn) return launch_impl<false, true>(tmA, tmB, p, grid, smem, stream);
-  if (a_mn && b_mn) return launch_impl<true, true>(tmA, tmB, p, grid, smem, stream);
-  return launch_impl<true, false>(tmA, tmB, p, grid, smem, stream);
+  // ---- staged (TMA-store) epilogue when the output geometry allows it
+  alignas(64) CUtensorMap tmO[3];
+  tmO[0] = tmO[1] = tmO[2] = tmA;
+  p.epi_tma = 0;
+  {
+    auto ok = [&](const void* ptr, int esz) {
+      if (ptr == nullptr) return true;
+      if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
+      if ((p.ldc * esz) % 16 != 0) return false;
+      if (p.kind == GEMM_PLAIN && p.nz1 > 1 && (p.c_z1_stride * esz) % 16 != 0) return false;
+      if (p.kind == GEMM_PLAIN && p.nz2 > 1 && (p.c_z2_stride * esz) % 16 != 0) return false;
+      return true;
+    };
+    const bool any_out = p.out_f32 != nullptr || p.out_f16 != nullptr || p.out_act_f16 != nullptr;
+    const bool shape_ok = (p.block_n % 64 == 0) || (n_tiles == 1);
+    if (!p.atomic && p.kind != GEMM_CONV_WGRAD && any_out && shape_ok && ok(p.out_f32, 4) && ok(p.out_f16, 2) &&
+        ok(p.out_act_f16, 2) && getenv("MDM_NO_TMA_EPILOGUE") == nullptr) {
+      auto mk = [&](void* ptr, int esz, uint32_t box0) {
+        TmapSpec o;
+        o.ptr = ptr;
+        if (p.kind == GEMM_CONV) {
+          o.dims[0] = p.N; o.dims[1] = p.W; o.dims[2] = p.H; o.dims[3] = p.nimg;
+          o.strides[0] = 1; o.strides[1] = p.ldc; o.strides[2] = static_cast<uint64_t>(p.W) * p.ldc;
+          o.strides[3] = static_cast<uint64_t>(p.H) * p.W * p.ldc;
+          o.box[0] = box0; o.box[1] = p.PW; o.box[2] = p.PH; o.box[3] = 1;
+        } else {
+          const uint64_t dflt = static_cast<uint64_t>(p.ldc) * p.M;
+          o.dims[0] = p.N; o.dims[1] = p.M; o.dims[2] = p.nz1; o.dims[3] = p.nz2;
+          o.strides[0] = 1; o.strides[1] = p.ldc;
+          o.strides[2] = p.nz1 > 1 ? static_cast<uint64_t>(p.c_z1_stride) : dflt;
+          o.strides[3] = p.nz2 > 1 ? static_cast<uint64_t>(p.c_z2_stride) : dflt;
+          o.box[0] = box0; o.box[1] = BLOCK_M; o.box[2] = 1; o.box[3] = 1;
+        }
+        (void)esz;
+        return o;
+      };
+      bool good = true;
+      if (p.out_f32 != nullptr) good = good && encode_tmap(&tmO[0], mk(p.out_f32, 4, 32), true) == 0;
+      if (p.out_f16 != nullptr) good = good && encode_tmap(&tmO[1], mk(p.out_f16, 2, 64), false) == 0;
+      if (p.out_act_f16 != nullptr) good = good && encode_tmap(&tmO[2], mk(p.out_act_f16, 2, 64), false) == 0;
+      if (good) {
+        p.epi_tma = 1;
+        const size_t need = (p.out_f32 ? 32768 : 0) + (p.out_f16 ? 16384 : 0) + (p.out_act_f16 ? 16384 : 0) + 1024;
+        if (smem < need) smem = need;
+      }
+    }
+  }
+
+  if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, tmO, p, grid, smem, stream);
+  if (!a_mn && b_mn) return launch_impl<false, true>(tmA, tmB, tmO, p, grid, smem, stream);
+  if (a_mn && b_mn) return launch_impl<true, true>(tmA, tmB, tmO, p, grid, smem, stream);
+  return launch_impl<true, false>(tmA, tmB, tmO, p, grid, smem, stream);
 }
 
 }  // namespace mdm

@@ -43,5 +43,7 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
 extern unsigned long long g_launch_count;
 extern bool g_profile;
 extern std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
+extern std::vector<mdm_gemm_params> g_profile_params;
+extern std::vector<int> g_profile_majors;
 
 }  // namespace mdm

@@ -61,6 +61,7 @@ class GemmParams(C.Structure):
         ("c_z2_stride", C.c_int64),
         ("act", C.c_int32),
         ("atomic", C.c_int32),
+        ("epi_tma", C.c_int32),
     ]
 
 

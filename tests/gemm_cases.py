@@ -205,7 +205,10 @@ CASES = [
     ("mnmn_split", lambda: run_plain(256, 128, 1024, 1, 1, 128, nsplit=4)),
     ("mnk_128", lambda: run_plain(256, 128, 256, 1, 0, 128)),
     ("mnmn_ragged", lambda: run_plain(200, 96, 328, 1, 1, 96)),
+    ("kk_multitile_epi", lambda: run_plain(300, 640, 192, 0, 0, 256, bias=True, residual=True, act=True, f16_out=True)),
+    ("kk_batched_epi", lambda: run_plain(130, 96, 64, 0, 0, 96, nz1=4, nz2=2, f16_out=True, residual=True)),
     ("conv_fwd_16", lambda: run_conv_fwd(2, 16, 16, 128, 128, 128)),
+    ("conv_fwd_ragged_hw", lambda: run_conv_fwd(3, 24, 24, 64, 192, 64)),
     ("conv_fwd_32", lambda: run_conv_fwd(1, 32, 32, 64, 256, 256)),
     ("conv_fwd_8", lambda: run_conv_fwd(2, 8, 8, 64, 64, 64)),
     ("conv_fwd_c96", lambda: run_conv_fwd(1, 16, 16, 96, 64, 64)),

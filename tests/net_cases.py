@@ -75,9 +75,9 @@ def run_case(kind, batch=2, tokens=6, dtype=torch.float64, verbose=True, res=Non
     grads = {}
     # Gradients that are mathematically zero (a conv bias feeding a GroupNorm whose groups are single
     # channels) come out as round-off on both sides: errors are measured against
-    # max(|ref_k|, 1e-3 * median_k max|ref_k|) so those are judged on the scale of real gradients.
+    # max(|ref_k|, 1e-2 * median_k max|ref_k|) so those are judged on the scale of real gradients.
     mags = sorted(float(P[k].grad.abs().max()) for k, _ in model.named_parameters())
-    floor = 1e-3 * mags[len(mags) // 2]
+    floor = 1e-2 * mags[len(mags) // 2]
     for k, p in model.named_parameters():
         ref = P[k].grad
         if p.grad is None:

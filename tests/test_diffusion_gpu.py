@@ -66,7 +66,7 @@ def test_get_loss_and_gradients(kind):
     oloss.mean().backward()
     assert nc.rel(loss.detach().cpu().double(), oloss.detach()) <= 5e-3
     mags = sorted(float(P[k].grad.abs().max()) for k in P)
-    floor = 1e-3 * mags[len(mags) // 2]
+    floor = 1e-2 * mags[len(mags) // 2]
     bad = {}
     for k, p in pipe.get_model().vision_model.named_parameters():
         ref = P[k].grad
