@@ -197,6 +197,20 @@ int mdm_avg_pool(const float* x, float* y, int planes, int H, int W, int ratio, 
 /* y = clip(x * scale, -1, 1) if clip else x * scale  (Sampler._postprocess, samplers.py:580-599) */
 int mdm_clip_scale(const float* x, float scale, int clip, float* y, int64_t numel, mdm_stream_t stream);
 
+
+/* ---------------------------------------------------------------- fused attention (single operator, for tests)
+ * SelfAttention.attention of both branches (models/unet.py:276-294,300-307): qkv16 (B*T, 3C) fp16 = [q|k|v]
+ * channel thirds, kv16 (B*S, 2C) fp16 = [k_c|v_c] or NULL, mask (B,S) fp32 or NULL.
+ * h16 (B*T, C) = softmax(qk^T/sqrt d) v + softmax(qk_c^T/sqrt d) v_c.  stats (B,heads,2,T,2) fp32 and
+ * oself16 are the forward's residue for the backward (may be NULL for inference). */
+int mdm_op_attention_fwd(const void* qkv16, const void* kv16, const float* mask, int B, int T, int S, int C, int heads,
+                         void* h16, void* oself16, float* stats, mdm_stream_t stream);
+/* Backward: dO16 (B*T, C) -> dqkv16 (B*T, 3C) and dkv16 (B*S, 2C). Dterm (B,heads,2,T) and dq32 (B*T, C) are
+ * fp32 scratch. */
+int mdm_op_attention_bwd(const void* qkv16, const void* kv16, const float* mask, const void* dO16, const void* h16,
+                         const void* oself16, const float* stats, int B, int T, int S, int C, int heads, float* Dterm,
+                         float* dq32, void* dqkv16, void* dkv16, mdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,4 +124,11 @@ struct Engine {
                      int Cout, float* packed_out);
 };
 
+// Fused attention (attention.cu)
+void attention_forward(const __half* qkv, const __half* kv, const float* mask, int B, int T, int S, int C, int heads,
+                       __half* h16, __half* oself16, float* stats, cudaStream_t st);
+void attention_backward(const __half* qkv, const __half* kv, const float* mask, const __half* dO, const __half* h16,
+                        const __half* oself16, const float* stats, int B, int T, int S, int C, int heads, float* Dterm,
+                        float* dq32, __half* dqkv16, __half* dkv16, cudaStream_t st);
+
 }  // namespace mdm

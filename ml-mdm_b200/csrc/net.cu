@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -63,6 +64,7 @@ struct Net {
   std::unordered_map<std::string, int> pindex;
   Engine eng;
   bool weights_dirty = true;
+  bool fused_attention = getenv("MDM_UNFUSED_ATTENTION") == nullptr;
   bool have_tape = false;
   std::vector<void*> persistent;  // cudaMalloc'd for the life of the net
   std::unordered_map<std::string, Act*> debug_acts;
@@ -612,37 +614,15 @@ struct Net {
     }
     const int Tp = round8(T);
     const long long nrow = static_cast<long long>(B) * nh * T;
-    float* sc = E.alloc<float>(nrow * Tp);
-    __half* Pm = E.alloc<__half>(nrow * Tp);
-    BOp Q{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 0, false};
-    BOp Kk = Q;
-    Kk.z_off = nh;
-    BOp Vm{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 2 * nh, true};
-    {
-      Epi e;
-      e.alpha = alpha;
-      e.out_f32 = sc;
-      gemm_batched(Q, Kk, T, T, d, nh, B, e, Tp, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp);
-    }
-    softmax_rows(sc, Pm, nrow, T, Tp, nullptr, 1, E.st);
-    E.pool.release(sc);
-    BOp Pk{Pm, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, false};
-    __half* h16 = E.alloc<__half>(rows * C);
-    float* hs32 = nullptr;
-    // cross-attention state
     const bool cross = a.cond;
     const int S = cs.S, cd = cs.cd, Sp = round8(S);
-    __half *cn16 = nullptr, *kv = nullptr, *Pc = nullptr;
-    float* lnstats = nullptr;
-    if (!cross) {
-      Epi e;
-      e.out_f16 = h16;
-      gemm_batched(Pk, Vm, T, d, T, nh, B, e, C, d, static_cast<long long>(T) * C);
-    } else {
-      hs32 = E.alloc<float>(rows * C);
-      Epi e;
-      e.out_f32 = hs32;
-      gemm_batched(Pk, Vm, T, d, T, nh, B, e, C, d, static_cast<long long>(T) * C);
+    const bool fused = fused_attention && d <= 128;
+    __half* h16 = E.alloc<__half>(rows * C);
+    __half *Pm = nullptr, *cn16 = nullptr, *kv = nullptr, *Pc = nullptr, *oself = nullptr;
+    float *lnstats = nullptr, *astats = nullptr;
+    BOp Q{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 0, false};
+    if (cross) {
+      // k_c, v_c = kv_cond(LayerNorm(cond))  (unet.py:304-305)
       Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
       Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
       const long long crow = static_cast<long long>(B) * S;
@@ -650,32 +630,62 @@ struct Net {
       lnstats = E.alloc<float>(crow * 2);
       layernorm_fwd(cs.cond32, lw.w, lb.w, cn16, lnstats, crow, cd, E.st);
       kv = E.alloc<__half>(crow * 2 * C);
-      {
-        Epi e2;
-        e2.bias = kb.w;
-        e2.out_f16 = kv;
-        E.gemm_nt(cn16, cd, kw.w16, cd, static_cast<int>(crow), 2 * C, cd, e2);
+      Epi e2;
+      e2.bias = kb.w;
+      e2.out_f16 = kv;
+      E.gemm_nt(cn16, cd, kw.w16, cd, static_cast<int>(crow), 2 * C, cd, e2);
+    }
+    if (fused) {
+      if (E.training) {
+        astats = E.alloc<float>(static_cast<long long>(B) * nh * 2 * T * 2);
+        if (cross) oself = E.alloc<__half>(rows * C);
       }
-      float* scc = E.alloc<float>(nrow * Sp);
-      Pc = E.alloc<__half>(nrow * Sp);
-      BOp Kc{kv, d, S, 2ll * C, 2 * nh, d, static_cast<long long>(S) * 2 * C, 0, false};
-      BOp Vc{kv, d, S, 2ll * C, 2 * nh, d, static_cast<long long>(S) * 2 * C, nh, true};
+      attention_forward(qkv, kv, cross ? cs.cross_mask : nullptr, B, T, S, C, nh, h16, oself, astats, E.st);
+    } else {
+      float* sc = E.alloc<float>(nrow * Tp);
+      Pm = E.alloc<__half>(nrow * Tp);
+      BOp Kk = Q;
+      Kk.z_off = nh;
+      BOp Vm{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 2 * nh, true};
       {
-        Epi e3;
-        e3.alpha = alpha;
-        e3.out_f32 = scc;
-        gemm_batched(Q, Kc, T, S, d, nh, B, e3, Sp, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp);
+        Epi e;
+        e.alpha = alpha;
+        e.out_f32 = sc;
+        gemm_batched(Q, Kk, T, T, d, nh, B, e, Tp, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp);
       }
-      softmax_rows(scc, Pc, nrow, S, Sp, cs.cross_mask, static_cast<long long>(nh) * T, E.st);
-      E.pool.release(scc);
-      BOp Pck{Pc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, false};
-      {
-        Epi e4;
-        e4.residual = hs32;
-        e4.out_f16 = h16;
-        gemm_batched(Pck, Vc, T, d, S, nh, B, e4, C, d, static_cast<long long>(T) * C);
+      softmax_rows(sc, Pm, nrow, T, Tp, nullptr, 1, E.st);
+      E.pool.release(sc);
+      BOp Pk{Pm, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, false};
+      if (!cross) {
+        Epi e;
+        e.out_f16 = h16;
+        gemm_batched(Pk, Vm, T, d, T, nh, B, e, C, d, static_cast<long long>(T) * C);
+      } else {
+        float* hs32 = E.alloc<float>(rows * C);
+        Epi e;
+        e.out_f32 = hs32;
+        gemm_batched(Pk, Vm, T, d, T, nh, B, e, C, d, static_cast<long long>(T) * C);
+        float* scc = E.alloc<float>(nrow * Sp);
+        Pc = E.alloc<__half>(nrow * Sp);
+        BOp Kc{kv, d, S, 2ll * C, 2 * nh, d, static_cast<long long>(S) * 2 * C, 0, false};
+        BOp Vc{kv, d, S, 2ll * C, 2 * nh, d, static_cast<long long>(S) * 2 * C, nh, true};
+        {
+          Epi e3;
+          e3.alpha = alpha;
+          e3.out_f32 = scc;
+          gemm_batched(Q, Kc, T, S, d, nh, B, e3, Sp, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp);
+        }
+        softmax_rows(scc, Pc, nrow, S, Sp, cs.cross_mask, static_cast<long long>(nh) * T, E.st);
+        E.pool.release(scc);
+        BOp Pck{Pc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, false};
+        {
+          Epi e4;
+          e4.residual = hs32;
+          e4.out_f16 = h16;
+          gemm_batched(Pck, Vc, T, d, S, nh, B, e4, C, d, static_cast<long long>(T) * C);
+        }
+        E.pool.release(hs32);
       }
-      E.pool.release(hs32);
     }
     Act* x1 = E.new_act(B, H, W, C);
     {
@@ -715,6 +725,7 @@ struct Net {
     if (!E.training) {
       E.pool.release(g1.y16); E.pool.release(g1.sums); E.pool.release(qkv); E.pool.release(Pm);
       E.pool.release(h16); E.pool.release(cn16); E.pool.release(lnstats); E.pool.release(kv); E.pool.release(Pc);
+      E.pool.release(oself); E.pool.release(astats);
       if (a.ffn) {
         E.pool.release(g2.y16); E.pool.release(g2.sums); E.pool.release(u16); E.pool.release(gl16);
         E.pool.release(x1->p);
@@ -767,91 +778,108 @@ struct Net {
       }
       E.pool.release(d16);
       __half* dqkv = E.alloc<__half>(rows * 3 * C);
-      BOp Q{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 0, false};
-      BOp Qm = Q; Qm.mn = true;
-      BOp Kk = Q; Kk.z_off = nh;
-      BOp Km = Kk; Km.mn = true;
-      BOp Vk = Q; Vk.z_off = 2 * nh;
-      BOp dHk{dh16, d, T, C, nh, d, static_cast<long long>(T) * C, 0, false};
-      BOp dHm = dHk; dHm.mn = true;
-      BOp Pmn{Pm, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, true};
-      const long long qkv_b = static_cast<long long>(T) * 3 * C;
-      // dV = P^T dH
-      {
-        Epi e;
-        e.out_f16 = dqkv + 2 * C;
-        gemm_batched(Pmn, dHm, T, d, T, nh, B, e, 3 * C, d, qkv_b);
-      }
-      // dP = dH V^T ; dS = softmax'(P, dP) * alpha
-      float* dP = E.alloc<float>(nrow * Tp);
-      {
-        Epi e;
-        e.out_f32 = dP;
-        gemm_batched(dHk, Vk, T, T, d, nh, B, e, Tp, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp);
-      }
-      __half* dS = E.alloc<__half>(nrow * Tp);
-      softmax_bwd_rows(Pm, dP, dS, nrow, T, Tp, alpha, E.st);
-      E.pool.release(dP);
-      BOp dSk{dS, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, false};
-      BOp dSm = dSk; dSm.mn = true;
+      __half* dkv = nullptr;
       float* dq32 = nullptr;
-      // dQ = dS K (+ cross term below)
-      if (cross) {
-        // fp32 partial in the same (ld = 3C) layout as dqkv so the cross term can add it as a residual
-        dq32 = E.alloc<float>(rows * 3 * C);
-        Epi e;
-        e.out_f32 = dq32;
-        gemm_batched(dSk, Km, T, d, T, nh, B, e, 3 * C, d, qkv_b);
+      if (fused) {
+        const long long crow = static_cast<long long>(B) * S;
+        if (cross) dkv = E.alloc<__half>(crow * 2 * C);
+        float* Dterm = E.alloc<float>(static_cast<long long>(B) * nh * 2 * T);
+        dq32 = E.alloc<float>(rows * C);
+        attention_backward(qkv, kv, cross ? cs.cross_mask : nullptr, dh16, h16, oself, astats, B, T, S, C, nh, Dterm, dq32,
+                           dqkv, dkv, E.st);
+        E.pool.release(Dterm);
       } else {
-        Epi e;
-        e.out_f16 = dqkv;
-        gemm_batched(dSk, Km, T, d, T, nh, B, e, 3 * C, d, qkv_b);
+        BOp Q{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 0, false};
+        BOp Qm = Q; Qm.mn = true;
+        BOp Kk = Q; Kk.z_off = nh;
+        BOp Km = Kk; Km.mn = true;
+        BOp Vk = Q; Vk.z_off = 2 * nh;
+        BOp dHk{dh16, d, T, C, nh, d, static_cast<long long>(T) * C, 0, false};
+        BOp dHm = dHk; dHm.mn = true;
+        BOp Pmn{Pm, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, true};
+        const long long qkv_b = static_cast<long long>(T) * 3 * C;
+        // dV = P^T dH
+        {
+          Epi e;
+          e.out_f16 = dqkv + 2 * C;
+          gemm_batched(Pmn, dHm, T, d, T, nh, B, e, 3 * C, d, qkv_b);
+        }
+        // dP = dH V^T ; dS = softmax'(P, dP) * alpha
+        float* dP = E.alloc<float>(nrow * Tp);
+        {
+          Epi e;
+          e.out_f32 = dP;
+          gemm_batched(dHk, Vk, T, T, d, nh, B, e, Tp, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp);
+        }
+        __half* dS = E.alloc<__half>(nrow * Tp);
+        softmax_bwd_rows(Pm, dP, dS, nrow, T, Tp, alpha, E.st);
+        E.pool.release(dP);
+        BOp dSk{dS, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, false};
+        BOp dSm = dSk; dSm.mn = true;
+        // dQ = dS K (+ cross term below)
+        if (cross) {
+          // fp32 partial in the same (ld = 3C) layout as dqkv so the cross term can add it as a residual
+          dq32 = E.alloc<float>(rows * 3 * C);
+          Epi e;
+          e.out_f32 = dq32;
+          gemm_batched(dSk, Km, T, d, T, nh, B, e, 3 * C, d, qkv_b);
+        } else {
+          Epi e;
+          e.out_f16 = dqkv;
+          gemm_batched(dSk, Km, T, d, T, nh, B, e, 3 * C, d, qkv_b);
+        }
+        // dK = dS^T Q
+        {
+          Epi e;
+          e.out_f16 = dqkv + C;
+          gemm_batched(dSm, Qm, T, d, T, nh, B, e, 3 * C, d, qkv_b);
+        }
+        E.pool.release(dS);
+        if (cross) {
+          Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
+          Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
+          const long long crow = static_cast<long long>(B) * S;
+          const long long kv_b = static_cast<long long>(S) * 2 * C;
+          dkv = E.alloc<__half>(crow * 2 * C);
+          BOp Kc{kv, d, S, 2ll * C, 2 * nh, d, kv_b, 0, false};
+          BOp Kcm = Kc; Kcm.mn = true;
+          BOp Vck = Kc; Vck.z_off = nh;
+          BOp Pcm{Pc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, true};
+          {  // dVc = Pc^T dH
+            Epi e;
+            e.out_f16 = dkv + C;
+            gemm_batched(Pcm, dHm, S, d, T, nh, B, e, 2 * C, d, kv_b);
+          }
+          float* dPc = E.alloc<float>(nrow * Sp);
+          {
+            Epi e;
+            e.out_f32 = dPc;
+            gemm_batched(dHk, Vck, T, S, d, nh, B, e, Sp, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp);
+          }
+          __half* dSc = E.alloc<__half>(nrow * Sp);
+          softmax_bwd_rows(Pc, dPc, dSc, nrow, S, Sp, alpha, E.st);
+          E.pool.release(dPc);
+          BOp dSck{dSc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, false};
+          BOp dScm = dSck; dScm.mn = true;
+          {  // dQ = dq32 + dSc Kc -> fp16
+            Epi e;
+            e.residual = dq32;
+            e.out_f16 = dqkv;
+            gemm_batched(dSck, Kcm, T, d, S, nh, B, e, 3 * C, d, qkv_b);
+          }
+          {  // dKc = dSc^T Q
+            Epi e;
+            e.out_f16 = dkv;
+            gemm_batched(dScm, Qm, S, d, T, nh, B, e, 2 * C, d, kv_b);
+          }
+          E.pool.release(dSc);
+        }
+
       }
-      // dK = dS^T Q
-      {
-        Epi e;
-        e.out_f16 = dqkv + C;
-        gemm_batched(dSm, Qm, T, d, T, nh, B, e, 3 * C, d, qkv_b);
-      }
-      E.pool.release(dS);
       if (cross) {
         Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
         Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
         const long long crow = static_cast<long long>(B) * S;
-        const long long kv_b = static_cast<long long>(S) * 2 * C;
-        __half* dkv = E.alloc<__half>(crow * 2 * C);
-        BOp Kc{kv, d, S, 2ll * C, 2 * nh, d, kv_b, 0, false};
-        BOp Kcm = Kc; Kcm.mn = true;
-        BOp Vck = Kc; Vck.z_off = nh;
-        BOp Pcm{Pc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, true};
-        {  // dVc = Pc^T dH
-          Epi e;
-          e.out_f16 = dkv + C;
-          gemm_batched(Pcm, dHm, S, d, T, nh, B, e, 2 * C, d, kv_b);
-        }
-        float* dPc = E.alloc<float>(nrow * Sp);
-        {
-          Epi e;
-          e.out_f32 = dPc;
-          gemm_batched(dHk, Vck, T, S, d, nh, B, e, Sp, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp);
-        }
-        __half* dSc = E.alloc<__half>(nrow * Sp);
-        softmax_bwd_rows(Pc, dPc, dSc, nrow, S, Sp, alpha, E.st);
-        E.pool.release(dPc);
-        BOp dSck{dSc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, false};
-        BOp dScm = dSck; dScm.mn = true;
-        {  // dQ = dq32 + dSc Kc -> fp16
-          Epi e;
-          e.residual = dq32;
-          e.out_f16 = dqkv;
-          gemm_batched(dSck, Kcm, T, d, S, nh, B, e, 3 * C, d, qkv_b);
-        }
-        {  // dKc = dSc^T Q
-          Epi e;
-          e.out_f16 = dkv;
-          gemm_batched(dScm, Qm, S, d, T, nh, B, e, 2 * C, d, kv_b);
-        }
-        E.pool.release(dSc);
         float* dcn = E.alloc<float>(crow * cd);
         linear_bwd(dkv, 2 * C, static_cast<int>(crow), 2 * C, cd, cn16, cd, kw, &kb, true, dcn, 0);
         E.pool.release(dkv);
