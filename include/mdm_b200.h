@@ -71,6 +71,7 @@ typedef struct mdm_gemm_params {
   int32_t act;
   int32_t atomic;
   int32_t epi_tma; /* filled by the launcher: staged shared-memory + TMA-store epilogue in use */
+  const void* gelu_grad_src; /* optional __half*, indexed like the output: result *= gelu'(src) (FFN backward) */
 } mdm_gemm_params;
 
 /* Measurement aid for bench.py's roofline leg: while enabled every launch of the tcgen05 GEMM kernel

@@ -126,6 +126,7 @@ void fill_epi(GemmParams& p, const Epi& e, long long dense_ld) {
   p.out_f16 = e.out_f16;
   p.out_act_f16 = e.out_act_f16;
   p.act = e.act;
+  p.gelu_grad_src = e.gelu_grad_src;
   p.ldc = e.ldc > 0 ? e.ldc : dense_ld;
 }
 

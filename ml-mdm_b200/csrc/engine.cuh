@@ -85,6 +85,7 @@ struct Epi {
   int act = 0;
   long long ldc = 0;  // 0: dense
   bool atomic_ok = false;  // out_f32 is zero-initialised (or accumulating) and split-K may be used
+  const __half* gelu_grad_src = nullptr;  // result *= gelu'(src[row][col])
 };
 
 struct Engine {

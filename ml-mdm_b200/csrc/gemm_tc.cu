@@ -45,6 +45,19 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return 0.5f * v * (1.0f + erf_v);
 }
 
+// d/dv of the exact-erf GELU, same erf approximation as gelu_erf
+__device__ __forceinline__ float gelu_grad(float v) {
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float ex = __expf(-x * x);
+  const float erf_v = copysignf(1.0f - poly * t * ex, v);
+  return 0.5f * (1.0f + erf_v) + v * 0.39894228040143267794f * ex;  // cdf + v * pdf
+}
+
 constexpr int NUM_THREADS = 256;  // warps 0-3: TMA / MMA / epilogue, warps 4-7: epilogue only
 
 template <bool A_MN, bool B_MN>
@@ -276,6 +289,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (col0 + j < p.N) v[j] += __ldg(p.residual + off0 + j);
           }
         }
+        if (p.gelu_grad_src != nullptr && valid && col0 < p.N) {
+          const __half* gp = reinterpret_cast<const __half*>(p.gelu_grad_src) + row_off + col0;
+          if (col0 + 16 <= p.N && (((row_off + col0) & 7) == 0)) {
+            const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(gp));
+            const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
+            const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 a = __half22float2(h0[q]), b2 = __half22float2(h1[q]);
+              v[2 * q] *= gelu_grad(a.x);
+              v[2 * q + 1] *= gelu_grad(a.y);
+              v[8 + 2 * q] *= gelu_grad(b2.x);
+              v[8 + 2 * q + 1] *= gelu_grad(b2.y);
+            }
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) v[j] *= gelu_grad(__half2float(gp[j]));
+          }
+        }
         if (p.out_f32 != nullptr) {
           uint8_t* base = st32 + (cc >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -360,6 +393,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 16; ++j)
           if (col0 + j < p.N) v[j] += __ldg(p.residual + off0 + j);
       }
+    }
+    if (p.gelu_grad_src != nullptr) {
+      const __half* gp = reinterpret_cast<const __half*>(p.gelu_grad_src) + off0;
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.N) v[j] *= gelu_grad(__half2float(gp[j]));
     }
     if (p.atomic) {
       for (int j = 0; j < 16; ++j)

@@ -3,6 +3,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 #include "gemm_tc.cuh"  // g_launch_count
 
 namespace mdm {
@@ -406,49 +408,46 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
 }
 
 // ------------------------------------------------------------------ casts and column sums
-template <bool IN_F16, int NL>
+template <bool IN_F16>
 __global__ void __launch_bounds__(TPB)
 cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, long long rows, int C,
                    float* __restrict__ colsum, const float* __restrict__ inv_scale) {
-  const LaneMap m = lane_map(C);
+  // blockIdx.y: tile of up to 4*TPB channels (one float4 lane per thread); blockIdx.x: row chunk
+  const int c0 = blockIdx.y * (4 * TPB);
+  const int Ct = min(C - c0, 4 * TPB);
+  const LaneMap m = lane_map(Ct);
   const long long per = cdiv(rows, gridDim.x);
   const long long r_begin = blockIdx.x * per;
   const long long r_end = min(rows, r_begin + per);
   if (!m.active) return;
-  float4 s[NL];
+  float4 s = make_float4(0, 0, 0, 0);
+  const int c = c0 + 4 * m.t_lane;
+  for (long long r = r_begin + m.sub; r < r_end; r += 2 * m.ppi) {
+    float4 v[2];
 #pragma unroll
-  for (int j = 0; j < NL; ++j) s[j] = make_float4(0, 0, 0, 0);
-  for (long long r = r_begin + m.sub; r < r_end; r += m.ppi) {
-#pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      const int l = m.t_lane + j * m.stride;
-      if (l < m.lanes) {
-        float4 v;
+    for (int u = 0; u < 2; ++u) {
+      const long long rr = r + static_cast<long long>(u) * m.ppi;
+      v[u] = make_float4(0, 0, 0, 0);
+      if (rr < r_end) {
         if (IN_F16) {
-          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(in_) + r * C + 4 * l));
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(in_) + rr * C + c));
           const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
           const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-          v = make_float4(a.x, a.y, b.x, b.y);
+          v[u] = make_float4(a.x, a.y, b.x, b.y);
         } else {
-          v = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in_) + r * C + 4 * l));
-          if (out16 != nullptr) st_half4(out16 + r * C + 4 * l, v.x, v.y, v.z, v.w);
+          v[u] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in_) + rr * C + c));
+          if (out16 != nullptr) st_half4(out16 + rr * C + c, v[u].x, v[u].y, v[u].z, v[u].w);
         }
-        s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
       }
     }
+    s.x += v[0].x + v[1].x; s.y += v[0].y + v[1].y; s.z += v[0].z + v[1].z; s.w += v[0].w + v[1].w;
   }
   if (colsum == nullptr) return;
   const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
-#pragma unroll
-  for (int j = 0; j < NL; ++j) {
-    const int l = m.t_lane + j * m.stride;
-    if (l < m.lanes) {
-      atomicAdd(colsum + 4 * l + 0, inv * s[j].x);
-      atomicAdd(colsum + 4 * l + 1, inv * s[j].y);
-      atomicAdd(colsum + 4 * l + 2, inv * s[j].z);
-      atomicAdd(colsum + 4 * l + 3, inv * s[j].w);
-    }
-  }
+  atomicAdd(colsum + c + 0, inv * s.x);
+  atomicAdd(colsum + c + 1, inv * s.y);
+  atomicAdd(colsum + c + 2, inv * s.z);
+  atomicAdd(colsum + c + 3, inv * s.w);
 }
 
 __global__ void cast_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
@@ -1009,19 +1008,22 @@ void gn_bwd_apply(const Src2& x, const float* dy, int N, int HW, int G, const fl
   MDM_LAUNCHED();
 }
 
+static dim3 colsum_grid(long long rows, int C) {
+  const int ctiles = static_cast<int>(cdiv(C, 4 * TPB));
+  const int Ct = std::min(C, 4 * TPB);
+  long long chunks = cdiv(rows, 2ll * host_ppi(Ct));
+  const long long cap = std::max<long long>(1, (148 * 8) / ctiles);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  return dim3(static_cast<unsigned>(chunks), ctiles);
+}
 void cast_colsum(const float* in, __half* out16, long long rows, int C, float* colsum, const float* inv_scale,
                  cudaStream_t st) {
-  long long chunks = cdiv(rows, host_ppi(C));
-  if (chunks > 148 * 8) chunks = 148 * 8;
-  MDM_DISPATCH_NL(C, (cast_colsum_kernel<false, NL><<<static_cast<int>(chunks), TPB, 0, st>>>(in, out16, rows, C, colsum,
-                                                                                             inv_scale)));
+  cast_colsum_kernel<false><<<colsum_grid(rows, C), TPB, 0, st>>>(in, out16, rows, C, colsum, inv_scale);
   MDM_LAUNCHED();
 }
 void colsum_f16(const __half* in, long long rows, int C, float* colsum, const float* inv_scale, cudaStream_t st) {
-  long long chunks = cdiv(rows, host_ppi(C));
-  if (chunks > 148 * 8) chunks = 148 * 8;
-  MDM_DISPATCH_NL(C, (cast_colsum_kernel<true, NL><<<static_cast<int>(chunks), TPB, 0, st>>>(in, nullptr, rows, C, colsum,
-                                                                                            inv_scale)));
+  cast_colsum_kernel<true><<<colsum_grid(rows, C), TPB, 0, st>>>(in, nullptr, rows, C, colsum, inv_scale);
   MDM_LAUNCHED();
 }
 void cast_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st) {

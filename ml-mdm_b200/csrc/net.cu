@@ -745,12 +745,16 @@ struct Net {
         Param &fw3 = P(a.pre + ".ffn.3.weight"), &fb3 = P(a.pre + ".ffn.3.bias");
         __half* d16 = E.alloc<__half>(rows * C);
         cast_colsum(out->g, d16, rows, C, fb3.g, inv_scale(), E.st);
-        float* dg32 = E.alloc<float>(rows * 4 * C);
-        linear_bwd(d16, C, irows, C, 4 * C, gl16, 4 * C, fw3, nullptr, false, dg32, 0);
-        E.pool.release(d16);
+        // ffn.3 backward: weight gradient, then dU = (dY W3) * gelu'(U) straight out of the dgrad epilogue
+        linear_bwd(d16, C, irows, C, 4 * C, gl16, 4 * C, fw3, nullptr, false, nullptr, 0);
         __half* du16 = E.alloc<__half>(rows * 4 * C);
-        gelu_bwd(u16, dg32, du16, rows * 4 * C, E.st);
-        E.pool.release(dg32);
+        {
+          Epi e;
+          e.out_f16 = du16;
+          e.gelu_grad_src = u16;
+          E.gemm_nn(d16, C, fw3.w16, 4 * C, irows, 4 * C, C, e);
+        }
+        E.pool.release(d16);
         float* dm32 = E.alloc<float>(rows * C);
         linear_bwd(du16, 4 * C, irows, 4 * C, C, g2.y16, C, fw1, &fb1, true, dm32, 0);
         E.pool.release(du16);

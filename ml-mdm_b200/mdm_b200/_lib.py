@@ -62,6 +62,7 @@ class GemmParams(C.Structure):
         ("act", C.c_int32),
         ("atomic", C.c_int32),
         ("epi_tma", C.c_int32),
+        ("gelu_grad_src", C.c_void_p),
     ]
 
 
