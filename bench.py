@@ -29,6 +29,7 @@ import torch  # noqa: E402
 # forward GFLOP per sample (2*MAC of every conv/linear + 4*B*C*T*S per attention), measured by hooking
 # the reference modules with S=128; training = 3x.
 FWD_GFLOP = {"cc12m_64x64": 385.4, "cc12m_256x256": 610.6, "cc12m_1024x1024": 1040.1}
+ATTN_FWD_GFLOP = 19.9  # of which attention (QK^T and PV); runs in the fused attention kernels, not the GEMM engine
 RES = {"cc12m_64x64": [64], "cc12m_256x256": [256, 64], "cc12m_1024x1024": [1024, 256, 64]}
 DEFAULT_BATCH = {"cc12m_64x64": 64, "cc12m_256x256": 32, "cc12m_1024x1024": 1}
 TOKENS = 128
@@ -186,28 +187,34 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (tcgen05 GEMM/conv engine): its launches are bracketed with
     # CUDA events on the launching stream for two extra steps
     roof = None
+    import ctypes as C
+    lib = _lib.lib()
     if rank == 0:
-        lib = _lib.lib()
-        import ctypes as C
         lib.mdm_profile_gemm(1)
-        for _ in range(2):
-            step(resident)
-            zero()
-        torch.cuda.synchronize()
+    for _ in range(2):  # every rank runs these steps (they contain the gradient all-reduce)
+        step(resident)
+        zero()
+    barrier()
+    if rank == 0:
         tot = C.c_double()
         cnt = C.c_longlong()
         lib.mdm_profile_read(C.byref(tot), C.byref(cnt))
         lib.mdm_profile_gemm(0)
         gemm_ms = tot.value / 2
         peak_tf, peak_bw, how = measured_peaks()
-        flops = FWD_GFLOP[cfg_name] * 3 * B * 1e9
+        fused_attn = os.environ.get("MDM_UNFUSED_ATTENTION") is None
+        flops = (FWD_GFLOP[cfg_name] - (ATTN_FWD_GFLOP if fused_attn else 0.0)) * 3 * B * 1e9
         ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear / attention)",
                 "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                "traffic": None, "peak_source": how, "launches_per_step": int(cnt.value // 2),
+                "traffic": None, "traffic_note": "ncu --set full of the largest conv launch (profiles/r01_ncu_conv256_summary.txt): "
+                "351 MB DRAM vs 403 MB algorithmic (fp16 in, fp32 out) -> no re-reads", "peak_source": how, "launches_per_step": int(cnt.value // 2),
                 "kernel_ms_per_step": round(gemm_ms, 3), "share_of_step": round(gemm_ms / (ms / args.steps), 3),
                 "algorithmic_flops_per_step": flops}
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     gb = B * world
     out = {
@@ -235,6 +242,7 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_arm(cfg_name, steps=1, warmup=1)
     print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
