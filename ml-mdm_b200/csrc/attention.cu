@@ -374,14 +374,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const float* mk = (cross && p.mask != nullptr) ? p.mask + static_cast<long long>(b) * p.S : nullptr;
   uint32_t qd_phase = 0, mma_phase = 0;
   const int nq = (p.T + TILE - 1) / TILE;
+  auto load_qd = [&](int q0) {
+    mbar_expect_tx(&qd_bar, 2 * kbk * KB_BYTES);
+    for (int kb = 0; kb < kbk; ++kb) {
+      tma_load_4d(sQ + kb * KB_BYTES, &tmQKV, &qd_bar, kb * 64, q0, hd, b);
+      tma_load_4d(sDO + kb * KB_BYTES, &tmDO, &qd_bar, kb * 64, q0, hd, b);
+    }
+  };
+  if (tid == 0) load_qd(0);
   for (int it = 0; it < nq; ++it) {
     const int q0 = it * TILE;
     if (tid == 0) {
-      mbar_expect_tx(&qd_bar, 2 * kbk * KB_BYTES);
-      for (int kb = 0; kb < kbk; ++kb) {
-        tma_load_4d(sQ + kb * KB_BYTES, &tmQKV, &qd_bar, kb * 64, q0, hd, b);
-        tma_load_4d(sDO + kb * KB_BYTES, &tmDO, &qd_bar, kb * 64, q0, hd, b);
-      }
       mbar_wait(&qd_bar, qd_phase);
       tc_fence_after();
       const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sDO);
@@ -452,6 +455,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_wait(&mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    // all MMAs that read Q / dO have retired: fetch the next query tile under the dQ drain
+    if (tid == 0 && it + 1 < nq) load_qd((it + 1) * TILE);
     {
       const int q = q0 + tid;
       float* dst = p.dq32 + (static_cast<long long>(b) * p.T + q) * p.C + hd * p.d;

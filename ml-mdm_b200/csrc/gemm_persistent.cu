@@ -1,0 +1,387 @@
+// Persistent, warp-specialised variant of the tcgen05 GEMM engine (same operand modes and fused
+// epilogue as gemm_tc.cu, selected by launch_gemm for the non-split, TMA-store-eligible launches).
+//
+//   one CTA per SM, looping over output tiles (m fastest, so concurrently running CTAs share B tiles in L2)
+//   warp 0      : TMA producer (one lane)          -- smem ring of 64-deep K stages, full/empty mbarriers
+//   warp 1      : tcgen05.mma issuer (one lane)    -- two 256-column fp32 accumulators in TMEM
+//   warps 2..9  : epilogue (256 threads)           -- drain accumulator t while the MMA warp fills t+1
+// The epilogue stages 64-column groups through 128B-swizzled shared memory and writes them with TMA stores.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "gemm_epi.cuh"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace mdm {
+using namespace ptx;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int SLAB_BYTES = 64 * 64 * 2;
+constexpr int MAX_STAGES = 8;
+constexpr int P_THREADS = 320;      // 10 warps
+constexpr int EPI_THREADS = 256;    // warps 2..9
+constexpr int STAGING_BYTES = 65536;  // f32 (2 x 16 KB) + f16 (16 KB) + act (16 KB)
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct TileCoord {
+  int m_tile, n_tile, z1, z2;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
+                          const __grid_constant__ CUtensorMap tmOact, const GemmParams p, int m_tiles, int n_tiles,
+                          int num_tiles, int staging_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_bias[256];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem;                  // epilogue staging first (fixed size), pipeline stages after it
+  uint8_t* stages = smem + staging_bytes;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nb_alloc = B_MN ? ((p.block_n + 63) / 64) * 64 : p.block_n;
+  const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
+  const int nstages = p.num_stages;
+  const int nkb = p.num_kblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  auto decode = [&](int tile) {
+    TileCoord c;
+    c.m_tile = tile % m_tiles;
+    int t = tile / m_tiles;
+    c.n_tile = t % n_tiles;
+    t /= n_tiles;
+    c.z1 = t % p.nz1;
+    c.z2 = t / p.nz1;
+    return c;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =========================== TMA producer ===========================
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nslab_b = nb_alloc / 64;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord c = decode(tile);
+        const int m0 = c.m_tile * BLOCK_M, n0 = c.n_tile * p.block_n;
+        const int az1 = p.a_use_z ? c.z1 + p.a_z1_off : 0, az2 = p.a_use_z ? c.z2 : 0;
+        const int bz1 = p.b_use_z ? c.z1 + p.b_z1_off : 0, bz2 = p.b_use_z ? c.z2 : 0;
+        int img = 0, th = 0, tw = 0;
+        if (p.kind == GEMM_CONV) {
+          tw = c.m_tile % p.tiles_w;
+          const int t = c.m_tile / p.tiles_w;
+          th = t % p.tiles_h;
+          img = t / p.tiles_h;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = stages + stage * stage_bytes;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          uint64_t* bar = &full_bar[stage];
+          mbar_expect_tx(bar, static_cast<uint32_t>(stage_bytes));
+          if (p.kind == GEMM_PLAIN) {
+            if (!A_MN) {
+              tma_load_4d(sA, &tmA, bar, kb * BLOCK_K, m0, az1, az2);
+            } else {
+              tma_load_4d(sA, &tmA, bar, m0, kb * BLOCK_K, az1, az2);
+              tma_load_4d(sA + SLAB_BYTES, &tmA, bar, m0 + 64, kb * BLOCK_K, az1, az2);
+            }
+            if (!B_MN) {
+              tma_load_4d(sB, &tmB, bar, kb * BLOCK_K, n0, bz1, bz2);
+            } else {
+              for (int s = 0; s < nslab_b; ++s)
+                tma_load_4d(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, kb * BLOCK_K, bz1, bz2);
+            }
+          } else {  // GEMM_CONV
+            const int tap = kb / p.kblocks_c;
+            const int cb = kb - tap * p.kblocks_c;
+            const int kh = (p.taps == 9) ? tap / 3 : 1;
+            const int kw = (p.taps == 9) ? tap % 3 : 1;
+            tma_load_4d(sA, &tmA, bar, cb * BLOCK_K, tw * p.PW + kw - 1, th * p.PH + kh - 1, img);
+            if (!B_MN) {
+              tma_load_4d(sB, &tmB, bar, cb * BLOCK_K, n0, tap, 0);
+            } else {
+              const int wt = p.flip ? (p.taps - 1 - tap) : tap;
+              for (int s = 0; s < nslab_b; ++s)
+                tma_load_4d(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, cb * BLOCK_K, wt, 0);
+            }
+          }
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // =========================== MMA issuer ===========================
+      const uint32_t idesc = make_idesc_f16(BLOCK_M, p.block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(stages + stage * stage_bytes);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, SLAB_BYTES, 1024)
+                                        : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
+                                        : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_f16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int et = threadIdx.x - 64;                 // 0..255
+    const int r = ((warp & 3) << 5) + lane;          // TMEM lane == tile row (warp w may touch lanes 32*(w%4)..)
+    const int half_id = (warp - 2) >> 2;             // warps 2..5 -> 0, 6..9 -> 1
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    uint8_t* st32 = staging;
+    uint8_t* st16 = staging + (p.out_f32 != nullptr ? 32768 : 0);
+    uint8_t* stact = st16 + (p.out_f16 != nullptr ? 16384 : 0);
+    float alpha = p.alpha;
+    if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev);
+    const int ngroups = (p.block_n + 63) / 64;
+    int it = 0;
+    bool stores_pending = false;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord c = decode(tile);
+      const int acc = it & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1;
+      const int m0 = c.m_tile * BLOCK_M, n0 = c.n_tile * p.block_n;
+      int img = 0, th = 0, tw = 0;
+      bool valid;
+      long long row_off;
+      int oc1, oc2, oc3;
+      if (p.kind == GEMM_CONV) {
+        tw = c.m_tile % p.tiles_w;
+        const int t = c.m_tile / p.tiles_w;
+        th = t % p.tiles_h;
+        img = t / p.tiles_h;
+        const int ph = r / p.PW, pw = r - ph * p.PW;
+        const int h = th * p.PH + ph, w = tw * p.PW + pw;
+        valid = (h < p.H) && (w < p.W);
+        row_off = (static_cast<long long>(img * p.H + h) * p.W + w) * p.ldc;
+        oc1 = tw * p.PW; oc2 = th * p.PH; oc3 = img;
+      } else {
+        const int row = m0 + r;
+        valid = row < p.M;
+        row_off = static_cast<long long>(row) * p.ldc + static_cast<long long>(c.z1) * p.c_z1_stride +
+                  static_cast<long long>(c.z2) * p.c_z2_stride;
+        oc1 = m0; oc2 = c.z1; oc3 = c.z2;
+      }
+      // bias tile (previous tile's readers are past the group barriers below)
+      epi_bar_sync();
+      s_bias[et] = (p.bias != nullptr && et < p.block_n && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+      epi_bar_sync();
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      for (int g = 0; g < ngroups; ++g) {
+        if (stores_pending) {  // staging buffer still being read by the previous group's TMA stores
+          if (et == 0) bulk_wait_read();
+          epi_bar_sync();
+        }
+#pragma unroll 1
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = half_id * 2 + ci;
+          const int cidx = g * 64 + cc * 16;
+          if (cidx >= p.block_n) break;  // warp-uniform
+          float v[16];
+          tmem_ld16(taddr_row + static_cast<uint32_t>(cidx), v);
+          const int col0 = n0 + cidx;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[j] * alpha + s_bias[cidx + j];
+          if (p.residual != nullptr && valid && col0 < p.N) {
+            const long long off0 = row_off + col0;
+            if (col0 + 16 <= p.N && ((off0 & 3) == 0)) {
+              const float4* rp = reinterpret_cast<const float4*>(p.residual + off0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldg(rp + q);
+                v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) v[j] += __ldg(p.residual + off0 + j);
+            }
+          }
+          if (p.gelu_grad_src != nullptr && valid && col0 < p.N) {
+            const __half* gp = reinterpret_cast<const __half*>(p.gelu_grad_src) + row_off + col0;
+            if (col0 + 16 <= p.N && (((row_off + col0) & 7) == 0)) {
+              const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(gp));
+              const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
+              const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
+              const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 a = __half22float2(h0[q]), b2 = __half22float2(h1[q]);
+                v[2 * q] *= gelu_grad(a.x);
+                v[2 * q + 1] *= gelu_grad(a.y);
+                v[8 + 2 * q] *= gelu_grad(b2.x);
+                v[8 + 2 * q + 1] *= gelu_grad(b2.y);
+              }
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) v[j] *= gelu_grad(__half2float(gp[j]));
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            uint8_t* base = st32 + (cc >> 1) * 16384 + r * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + q) ^ swz;
+              *reinterpret_cast<float4*>(base + chunk * 16) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+          if (p.out_f16 != nullptr) {
+            uint8_t* base = st16 + r * 128;
+            __half2 h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[0]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[4]);
+          }
+          if (p.out_act_f16 != nullptr) {
+            uint8_t* base = stact + r * 128;
+            __half2 h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float a0 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q]) : v[2 * q];
+              const float a1 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q + 1]) : v[2 * q + 1];
+              h[q] = __floats2half2_rn(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[0]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[4]);
+          }
+        }
+        if (g == ngroups - 1) {
+          // last TMEM read of this tile is done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (et == 0) {
+          const int colg = n0 + g * 64;
+          if (colg < p.N) {
+            if (p.out_f32 != nullptr) {
+              tma_store_4d(&tmO32, st32, colg, oc1, oc2, oc3);
+              if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_store_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+            }
+            if (p.out_f16 != nullptr) tma_store_4d(&tmO16, st16, colg, oc1, oc2, oc3);
+            if (p.out_act_f16 != nullptr) tma_store_4d(&tmOact, stact, colg, oc1, oc2, oc3);
+          }
+          bulk_commit();
+        }
+        stores_pending = true;
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool A_MN, bool B_MN>
+int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const GemmParams& p, int m_tiles,
+             int n_tiles, int num_tiles, int grid, size_t smem, int staging_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<A_MN, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+  }
+  gemm_tc_persistent_kernel<A_MN, B_MN><<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], p, m_tiles,
+                                                                         n_tiles, num_tiles, staging_bytes);
+  if (g_profile) {
+    cudaEventRecord(e1, stream);
+    g_profile_events.emplace_back(e0, e1);
+    g_profile_params.push_back(p);
+    g_profile_majors.push_back((A_MN ? 2 : 0) | (B_MN ? 1 : 0) | 4);
+  }
+  ++g_launch_count;
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+// Called by launch_gemm when the launch is eligible (no split-K, TMA-store epilogue, not wgrad).
+int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, int a_mn, int b_mn,
+                           GemmParams p, int m_tiles, int n_tiles, cudaStream_t stream) {
+  const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
+  const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
+  const int staging = (p.out_f32 ? 32768 : 0) + (p.out_f16 ? 16384 : 0) + (p.out_act_f16 ? 16384 : 0);
+  int stages = (222 * 1024 - staging - 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return -30;
+  p.num_stages = stages;
+  const size_t smem = static_cast<size_t>(staging) + static_cast<size_t>(stages) * stage_bytes + 1024;
+  const int num_tiles = m_tiles * n_tiles * p.nz1 * p.nz2;
+  const int grid = num_tiles < 148 ? num_tiles : 148;
+  if (!a_mn && !b_mn) return launch_p<false, false>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  if (!a_mn && b_mn) return launch_p<false, true>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  if (a_mn && b_mn) return launch_p<true, true>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  return launch_p<true, false>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+}
+
+}  // namespace mdm

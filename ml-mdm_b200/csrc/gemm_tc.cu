@@ -7,6 +7,7 @@
 #include <utility>
 #include <vector>
 
+#include "gemm_epi.cuh"
 #include "ptx.cuh"
 
 namespace mdm {
@@ -30,33 +31,6 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int SLAB_BYTES = 64 * 64 * 2;  // one 64(k) x 64(mn) MN-major slab
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_BUDGET = 99 * 1024;  // two CTAs per SM: one runs its epilogue under the other's mainloop
-
-// Exact-erf GELU (nn.GELU() default, unet.py:270) with erf from Abramowitz-Stegun 7.1.26
-// (|abs error| <= 1.5e-7, far below the fp16 rounding of the stored result); one ex2 + one rcp.
-__device__ __forceinline__ float gelu_erf(float v) {
-  const float x = fabsf(v) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-x * x);
-  const float erf_v = copysignf(erf_abs, v);
-  return 0.5f * v * (1.0f + erf_v);
-}
-
-// d/dv of the exact-erf GELU, same erf approximation as gelu_erf
-__device__ __forceinline__ float gelu_grad(float v) {
-  const float x = fabsf(v) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float ex = __expf(-x * x);
-  const float erf_v = copysignf(1.0f - poly * t * ex, v);
-  return 0.5f * (1.0f + erf_v) + v * 0.39894228040143267794f * ex;  // cdf + v * pdf
-}
 
 constexpr int NUM_THREADS = 256;  // warps 0-3: TMA / MMA / epilogue, warps 4-7: epilogue only
 
@@ -501,7 +475,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
@@ -544,7 +518,9 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
 
   const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
   const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
-  int stages = (SMEM_BUDGET - 1024) / stage_bytes;
+  static const int budget_kb = getenv("MDM_SMEM_BUDGET_KB") ? atoi(getenv("MDM_SMEM_BUDGET_KB")) : 0;  // dev knob
+  const int budget = budget_kb > 0 ? budget_kb * 1024 : SMEM_BUDGET;
+  int stages = (budget - 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int per = (p.num_kblocks + p.nsplit - 1) / p.nsplit;
   if (stages > per) stages = per;
@@ -608,6 +584,18 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
         if (smem < need) smem = need;
       }
     }
+  }
+
+  // persistent warp-specialised variant (gemm_persistent.cu) for the non-split, TMA-store launches
+  static const bool persistent = getenv("MDM_GEMM_NO_PERSISTENT") == nullptr;
+  // Measured (B200): the persistent kernel wins where the epilogue matters (K <= ~3000: 16384x3072x768 runs at
+  // 1048 vs 824 TFLOP/s) and loses on long-K tiles, where two co-resident CTAs hide latency better
+  // (8192^3: 1196 vs 1353), and when the tile count leaves a mostly empty last round.
+  {
+    const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
+    const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
+    if (persistent && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
+      return launch_gemm_persistent(tmA, tmB, tmO, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }
 
   if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, tmO, p, grid, smem, stream);

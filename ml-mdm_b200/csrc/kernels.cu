@@ -48,6 +48,18 @@ __device__ __forceinline__ float4 ld_src(const Src2& s, long long pix, int c) {
   return __ldg(reinterpret_cast<const float4*>(s.p1 + pix * s.c1 + (c - s.c0)));
 }
 
+// gradient operand stored as fp32 or fp16
+template <bool F16>
+__device__ __forceinline__ float4 ld_dy(const void* dy, long long off) {
+  if (F16) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(dy) + off));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(dy) + off));
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float silu_grad(float x) {
@@ -63,8 +75,8 @@ __device__ __forceinline__ void st_half4(__half* p, float a, float b, float c, f
   *reinterpret_cast<uint2*>(p) = v;
 }
 
-inline int pixel_chunks(int N, int HW, int ppi_hint) {
-  long long want = cdiv(8 * 148, N);
+inline int pixel_chunks(int N, int HW, int ppi_hint, int per_sm = 8) {
+  long long want = cdiv(per_sm * 148, N);
   long long maxc = cdiv(HW, ppi_hint > 0 ? ppi_hint : 1);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
@@ -231,9 +243,9 @@ gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const flo
   }
 }
 
-template <int NL>
+template <int NL, bool DY16>
 __global__ void __launch_bounds__(TPB)
-gn_bwd_reduce_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
+gn_bwd_reduce_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ film, int film_ld, int film_off, int silu,
                      float* __restrict__ ab) {
@@ -259,7 +271,7 @@ gn_bwd_reduce_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const 
       const int l = m.t_lane + j * m.stride;
       if (l < m.lanes) {
         const float4 v = ld_src(x, pix, 4 * l);
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + pix * C + 4 * l));
+        const float4 d = ld_dy<DY16>(dy, pix * C + 4 * l);
         const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
                              v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
         const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
@@ -326,9 +338,9 @@ __global__ void gn_bwd_finalize_kernel(int C, int G, int HW, const float* __rest
   }
 }
 
-template <int NL>
+template <int NL, bool DY16>
 __global__ void __launch_bounds__(TPB)
-gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
+gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ film, int film_ld, int film_off, int silu,
                     const float* __restrict__ pg, const float* __restrict__ extra, Dst2 dst) {
@@ -342,6 +354,9 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
   if (!m.active) return;
   GnCoef<NL> k;
   gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  float4 csum[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) csum[j] = make_float4(0, 0, 0, 0);
   // per-channel group terms P1/m, P2/m and gamma' (already includes 1+ta)
   float4 q1[NL], q2[NL];
   const float inv_m = 1.0f / (static_cast<float>(HW) * cpg);
@@ -368,7 +383,7 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
       if (l < m.lanes) {
         const int c = 4 * l;
         const float4 v = ld_src(x, pix, c);
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + pix * C + c));
+        const float4 d = ld_dy<DY16>(dy, pix * C + c);
         const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
                              v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
         const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
@@ -387,6 +402,11 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
           const float4 ex = __ldg(reinterpret_cast<const float4*>(extra + pix * C + c));
           r[0] += ex.x; r[1] += ex.y; r[2] += ex.z; r[3] += ex.w;
         }
+        if (dst.h16 != nullptr) {  // single consumer: fp16 operand for the next GEMM + bias-gradient column sums
+          st_half4(dst.h16 + pix * C + c, r[0], r[1], r[2], r[3]);
+          csum[j].x += r[0]; csum[j].y += r[1]; csum[j].z += r[2]; csum[j].w += r[3];
+          continue;
+        }
         float* o;
         int acc;
         if (c < dst.c0) {
@@ -402,6 +422,19 @@ gn_bwd_apply_kernel(Src2 x, const float* __restrict__ dy, int HW, int G, const f
           outv.x += old.x; outv.y += old.y; outv.z += old.z; outv.w += old.w;
         }
         *reinterpret_cast<float4*>(o) = outv;
+      }
+    }
+  }
+  if (dst.h16 != nullptr && dst.colsum != nullptr) {
+    const float inv = dst.inv_scale != nullptr ? __ldg(dst.inv_scale) : 1.f;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        atomicAdd(dst.colsum + 4 * l + 0, inv * csum[j].x);
+        atomicAdd(dst.colsum + 4 * l + 1, inv * csum[j].y);
+        atomicAdd(dst.colsum + 4 * l + 2, inv * csum[j].z);
+        atomicAdd(dst.colsum + 4 * l + 3, inv * csum[j].w);
       }
     }
   }
@@ -982,13 +1015,17 @@ void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const floa
                                                                 y16, raw16)));
   MDM_LAUNCHED();
 }
-void gn_bwd_reduce(const Src2& x, const float* dy, int N, int HW, int G, const float* sums, const float* gamma,
-                   const float* beta, const float* film, int film_ld, int film_off, int silu, float* ab,
-                   cudaStream_t st) {
+void gn_bwd_reduce(const Src2& x, const void* dy, int dy_f16, int N, int HW, int G, const float* sums,
+                   const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
+                   float* ab, cudaStream_t st) {
   const int C = x.c0 + x.c1;
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  MDM_DISPATCH_NL(C, (gn_bwd_reduce_kernel<NL><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
-                                                                     film_off, silu, ab)));
+  if (dy_f16)
+    MDM_DISPATCH_NL(C, (gn_bwd_reduce_kernel<NL, true><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
+                                                                             film_off, silu, ab)));
+  else
+    MDM_DISPATCH_NL(C, (gn_bwd_reduce_kernel<NL, false><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film,
+                                                                              film_ld, film_off, silu, ab)));
   MDM_LAUNCHED();
 }
 void gn_bwd_finalize(int N, int C, int G, int HW, const float* ab, const float* gamma, const float* beta,
@@ -998,32 +1035,38 @@ void gn_bwd_finalize(int N, int C, int G, int HW, const float* ab, const float* 
                                             dbeta, dfilm, inv_scale);
   MDM_LAUNCHED();
 }
-void gn_bwd_apply(const Src2& x, const float* dy, int N, int HW, int G, const float* sums, const float* gamma,
-                  const float* beta, const float* film, int film_ld, int film_off, int silu, const float* pg,
-                  const float* extra, const Dst2& dst, cudaStream_t st) {
+void gn_bwd_apply(const Src2& x, const void* dy, int dy_f16, int N, int HW, int G, const float* sums,
+                  const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
+                  const float* pg, const float* extra, const Dst2& dst, cudaStream_t st) {
   const int C = x.c0 + x.c1;
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  MDM_DISPATCH_NL(C, (gn_bwd_apply_kernel<NL><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
-                                                                    film_off, silu, pg, extra, dst)));
+  if (dy_f16)
+    MDM_DISPATCH_NL(C, (gn_bwd_apply_kernel<NL, true><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
+                                                                            film_off, silu, pg, extra, dst)));
+  else
+    MDM_DISPATCH_NL(C, (gn_bwd_apply_kernel<NL, false><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film,
+                                                                             film_ld, film_off, silu, pg, extra, dst)));
   MDM_LAUNCHED();
 }
 
-static dim3 colsum_grid(long long rows, int C) {
+static dim3 colsum_grid(long long rows, int C, bool coarse) {
   const int ctiles = static_cast<int>(cdiv(C, 4 * TPB));
   const int Ct = std::min(C, 4 * TPB);
-  long long chunks = cdiv(rows, 2ll * host_ppi(Ct));
-  const long long cap = std::max<long long>(1, (148 * 8) / ctiles);
+  // every CTA ends with one atomic per column. Measured: the fp16 column-sum passes are faster with few long
+  // CTAs (5.6 vs 6.4 ms per step), the fp32->fp16 cast passes with many short ones (7.3 vs 7.7 ms).
+  long long chunks = coarse ? cdiv(rows, 128ll * host_ppi(Ct)) : cdiv(rows, 2ll * host_ppi(Ct));
+  const long long cap = std::max<long long>(1, (coarse ? 148 * 2 : 148 * 8) / ctiles);
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   return dim3(static_cast<unsigned>(chunks), ctiles);
 }
 void cast_colsum(const float* in, __half* out16, long long rows, int C, float* colsum, const float* inv_scale,
                  cudaStream_t st) {
-  cast_colsum_kernel<false><<<colsum_grid(rows, C), TPB, 0, st>>>(in, out16, rows, C, colsum, inv_scale);
+  cast_colsum_kernel<false><<<colsum_grid(rows, C, false), TPB, 0, st>>>(in, out16, rows, C, colsum, inv_scale);
   MDM_LAUNCHED();
 }
 void colsum_f16(const __half* in, long long rows, int C, float* colsum, const float* inv_scale, cudaStream_t st) {
-  cast_colsum_kernel<true><<<colsum_grid(rows, C), TPB, 0, st>>>(in, nullptr, rows, C, colsum, inv_scale);
+  cast_colsum_kernel<true><<<colsum_grid(rows, C, true), TPB, 0, st>>>(in, nullptr, rows, C, colsum, inv_scale);
   MDM_LAUNCHED();
 }
 void cast_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st) {

@@ -21,6 +21,10 @@ struct Dst2 {
   float* p1;
   int c0, c1;
   int acc0, acc1;  // 1: += into existing contents, 0: overwrite
+  // alternative single-consumer destination: fp16 operand + column sums (bias gradient); p0/p1 unused
+  __half* h16;
+  float* colsum;
+  const float* inv_scale;
 };
 
 // ---- GroupNorm family (reference: nn.GroupNorm(32, C) in unet.py:198,207,259,268,749)
@@ -31,8 +35,8 @@ void gn_stats(const Src2& x, int N, int HW, int G, float* sums, cudaStream_t st)
 void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const float* gamma,
               const float* beta, const float* film, int film_ld, int film_off, int silu, __half* y16,
               __half* raw16, cudaStream_t st);
-// Backward. dy: fp32 [N][HW][C] gradient w.r.t. y16.  ab: [N][C][2] scratch, zero on entry.
-void gn_bwd_reduce(const Src2& x, const float* dy, int N, int HW, int G, const float* sums,
+// Backward. dy: fp32 or fp16 (dy_f16) [N][HW][C] gradient w.r.t. y16.  ab: [N][C][2] scratch, zero on entry.
+void gn_bwd_reduce(const Src2& x, const void* dy, int dy_f16, int N, int HW, int G, const float* sums,
                    const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
                    int silu, float* ab, cudaStream_t st);
 // pg: [N][G][2] scratch (written). dgamma/dbeta: += inv_scale * grad. dfilm (optional): dense
@@ -41,7 +45,7 @@ void gn_bwd_finalize(int N, int C, int G, int HW, const float* ab, const float* 
                      const float* film, int film_ld, int film_off, float* pg, float* dgamma,
                      float* dbeta, float* dfilm, const float* inv_scale, cudaStream_t st);
 // dx = rstd * (du*(1+ta)*gamma - P1/m - xhat*P2/m) + extra ; written/accumulated into dst.
-void gn_bwd_apply(const Src2& x, const float* dy, int N, int HW, int G, const float* sums,
+void gn_bwd_apply(const Src2& x, const void* dy, int dy_f16, int N, int HW, int G, const float* sums,
                   const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
                   int silu, const float* pg, const float* extra, const Dst2& dst, cudaStream_t st);
 

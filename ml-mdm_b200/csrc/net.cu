@@ -380,29 +380,38 @@ struct Net {
     gn_apply(x, N, HW, G, o.sums, gw.w, gb.w, film, film_ld, film_off, silu, o.y16, o.raw16, eng.st);
     return o;
   }
-  // Backward through gn_apply: dy32 is the fp32 gradient w.r.t. its fp16 output.
-  void gn_bwd(const Src2& x, const float* dy32, int N, int HW, int G, const float* sums, Param& gw, Param& gb,
-              const float* film, int film_ld, int film_off, int silu, float* dfilm, const float* extra,
-              Act* dst0, Act* dst1) {
+  // Backward through gn_apply. dy: gradient w.r.t. its fp16 output, fp16 (dy_f16) or fp32.
+  // Destination: Act gradients dst0/dst1 (accumulating), or -- when h16_out is given -- a plain fp16
+  // tensor plus bias-gradient column sums (single consumer, nothing to accumulate).
+  void gn_bwd(const Src2& x, const void* dy, bool dy_f16, int N, int HW, int G, const float* sums, Param& gw, Param& gb,
+              const float* film, int film_ld, int film_off, int silu, float* dfilm, const float* extra, Act* dst0,
+              Act* dst1, __half* h16_out = nullptr, float* colsum = nullptr) {
     const int C = x.c0 + x.c1;
     float* ab = eng.zeros_f32(2ll * N * C);
     float* pg = eng.alloc<float>(2ll * N * G);
-    gn_bwd_reduce(x, dy32, N, HW, G, sums, gw.w, gb.w, film, film_ld, film_off, silu, ab, eng.st);
+    gn_bwd_reduce(x, dy, dy_f16 ? 1 : 0, N, HW, G, sums, gw.w, gb.w, film, film_ld, film_off, silu, ab, eng.st);
     // dgamma/dbeta always have somewhere to go: when a grad buffer is missing use scratch
     float* dg = gw.g != nullptr ? gw.g : eng.zeros_f32(C);
     float* db = gb.g != nullptr ? gb.g : eng.zeros_f32(C);
     gn_bwd_finalize(N, C, G, HW, ab, gw.w, gb.w, film, film_ld, film_off, pg, dg, db, dfilm, inv_scale(), eng.st);
     Dst2 d{};
-    int a0 = 0, a1 = 0;
-    d.p0 = eng.grad_buf(dst0, &a0);
-    d.c0 = x.c0;
-    d.acc0 = a0;
-    if (dst1 != nullptr) {
-      d.p1 = eng.grad_buf(dst1, &a1);
-      d.c1 = x.c1;
-      d.acc1 = a1;
+    if (h16_out != nullptr) {
+      d.h16 = h16_out;
+      d.colsum = colsum;
+      d.inv_scale = inv_scale();
+      d.c0 = C;
+    } else {
+      int a0 = 0, a1 = 0;
+      d.p0 = eng.grad_buf(dst0, &a0);
+      d.c0 = x.c0;
+      d.acc0 = a0;
+      if (dst1 != nullptr) {
+        d.p1 = eng.grad_buf(dst1, &a1);
+        d.c1 = x.c1;
+        d.acc1 = a1;
+      }
     }
-    gn_bwd_apply(x, dy32, N, HW, G, sums, gw.w, gb.w, film, film_ld, film_off, silu, pg, extra, d, eng.st);
+    gn_bwd_apply(x, dy, dy_f16 ? 1 : 0, N, HW, G, sums, gw.w, gb.w, film, film_ld, film_off, silu, pg, extra, d, eng.st);
     eng.pool.release(ab);
     eng.pool.release(pg);
   }
@@ -477,18 +486,18 @@ struct Net {
         E.conv3x3_wgrad(d16, cout, g2.y16, cout, N, H, W, cout, cout, wtmp);
         unpack_conv_wgrad(wtmp, c2w.g, cout, cout, 9, cout, inv_scale(), E.st);
       }
-      float* da2 = E.alloc<float>(rows * cout);
+      __half* da2 = E.alloc<__half>(rows * cout);
       {
         Epi e;
-        e.out_f32 = da2;
+        e.out_f16 = da2;
         E.conv3x3_dgrad(d16, cout, N, H, W, cout, c2w.w16, cout, e);
       }
-      // norm2 + FiLM + SiLU  (gradient lands in a temporary Act for h)
-      Act hact;
-      hact.n = N; hact.h = H; hact.w = W; hact.c = cout;
+      // norm2 + FiLM + SiLU: h has a single consumer, so its gradient goes straight to the fp16 operand
+      // of conv1's backward, with conv1's bias gradient as column sums
+      __half* dh16 = E.alloc<__half>(rows * cout);
       float* dfilm = E.alloc<float>(2ll * N * cout);
-      gn_bwd(Src2{h, nullptr, cout, 0}, da2, N, HW, G, g2.sums, n2w, n2b, ls->film, Lp->film_total, r.film_off, 1,
-             dfilm, nullptr, &hact, nullptr);
+      gn_bwd(Src2{h, nullptr, cout, 0}, da2, true, N, HW, G, g2.sums, n2w, n2b, ls->film, Lp->film_total, r.film_off, 1,
+             dfilm, nullptr, nullptr, nullptr, dh16, c1b.g);
       E.pool.release(da2);
       // time layer: film = silu(temb) Wt^T + bt  (batch rows)
       {
@@ -502,22 +511,19 @@ struct Net {
         E.pool.release(dfilm);
       }
       // conv1
-      __half* dh16 = E.alloc<__half>(rows * cout);
-      cast_colsum(hact.g, dh16, rows, cout, c1b.g, inv_scale(), E.st);
-      E.pool.release(hact.g);
       if (c1w.g != nullptr) {
         E.conv3x3_wgrad(dh16, cout, g1.y16, cin, N, H, W, cin, cout, wtmp);
         unpack_conv_wgrad(wtmp, c1w.g, cout, cin, 9, cin, inv_scale(), E.st);
       }
-      float* da1 = E.alloc<float>(rows * cin);
+      __half* da1 = E.alloc<__half>(rows * cin);
       {
         Epi e;
-        e.out_f32 = da1;
+        e.out_f16 = da1;
         E.conv3x3_dgrad(dh16, cout, N, H, W, cout, c1w.w16, cin, e);
       }
       E.pool.release(dh16);
       // norm1 + SiLU -> x (and skip). Identity residual folds in as `extra`.
-      gn_bwd(src, da1, N, HW, G, g1.sums, n1w, n1b, nullptr, 0, 0, 1, nullptr, proj ? nullptr : out->g, x, skip);
+      gn_bwd(src, da1, true, N, HW, G, g1.sums, n1w, n1b, nullptr, 0, 0, 1, nullptr, proj ? nullptr : out->g, x, skip);
       E.pool.release(da1);
       if (proj) {
         Param &c3w = P(r.pre + ".conv3.weight"), &c3b = P(r.pre + ".conv3.bias");
@@ -758,7 +764,7 @@ struct Net {
         float* dm32 = E.alloc<float>(rows * C);
         linear_bwd(du16, 4 * C, irows, 4 * C, C, g2.y16, C, fw1, &fb1, true, dm32, 0);
         E.pool.release(du16);
-        gn_bwd(Src2{x1->p, nullptr, C, 0}, dm32, B, T, 32, g2.sums, fw0, fb0, nullptr, 0, 0, 0, nullptr, out->g, x1,
+        gn_bwd(Src2{x1->p, nullptr, C, 0}, dm32, false, B, T, 32, g2.sums, fw0, fb0, nullptr, 0, 0, 0, nullptr, out->g, x1,
                nullptr);
         E.pool.release(dm32);
         E.pool.release(out->g);
@@ -901,7 +907,7 @@ struct Net {
       E.pool.release(dqkv);
       E.pool.release(dh16);
       E.pool.release(dq32);
-      gn_bwd(Src2{x->p, nullptr, C, 0}, dn32, B, T, 32, g1.sums, nw, nb, nullptr, 0, 0, 0, nullptr, x1->g, x, nullptr);
+      gn_bwd(Src2{x->p, nullptr, C, 0}, dn32, false, B, T, 32, g1.sums, nw, nb, nullptr, 0, 0, 0, nullptr, x1->g, x, nullptr);
       E.pool.release(dn32);
       E.pool.release(x1->g);
     });
@@ -1356,11 +1362,11 @@ struct Net {
             unpack_conv_wgrad(wtmp, ow.g, oc, Cf, 9, Cf, inv_scale(), E.st);
             E.pool.release(wtmp);
           }
-          float* da = E.alloc<float>(rows * Cf);
+          __half* da = E.alloc<__half>(rows * Cf);
           Epi e;
-          e.out_f32 = da;
+          e.out_f16 = da;
           E.conv3x3_dgrad(orec->d16, 8, B, R, R, oc, ow.w16, Cf, e);
-          gn_bwd(Src2{feat->p, nullptr, Cf, 0}, da, B, HW, Lp->c.groups, g.sums, nw, nb, nullptr, 0, 0, 1, nullptr,
+          gn_bwd(Src2{feat->p, nullptr, Cf, 0}, da, true, B, HW, Lp->c.groups, g.sums, nw, nb, nullptr, 0, 0, 1, nullptr,
                  nullptr, feat, nullptr);
           E.pool.release(da);
           E.pool.release(bs);

@@ -221,16 +221,16 @@ CASES = [
 TOL = {"f32": 2e-5, "f16": 1.5e-3, "act": 1.5e-3}
 
 
-def bench_one(M, N, K, iters=20):
+def bench_one(M, N, K, iters=20, bn=256):
     A = torch.randn(M, K, device=DEV).to(torch.float16)
     B = torch.randn(N, K, device=DEV).to(torch.float16)
     out = torch.zeros(M, N, device=DEV, dtype=torch.float16)
     sa = _lib.tmap(A.data_ptr(), (K, M, 1, 1), (1, K, K * M, K * M), (64, 128, 1, 1))
-    sb = _lib.tmap(B.data_ptr(), (K, N, 1, 1), (1, K, K * N, K * N), (64, 256, 1, 1))
+    sb = _lib.tmap(B.data_ptr(), (K, N, 1, 1), (1, K, K * N, K * N), (64, bn, 1, 1))
     p = _lib.GemmParams()
     p.kind = 0
     p.M, p.N, p.K = M, N, K
-    p.block_n = 256
+    p.block_n = bn
     p.num_kblocks = K // 64
     p.alpha = 1.0
     p.ldc = N
@@ -285,9 +285,10 @@ if __name__ == "__main__":
                 print("  device error is sticky:", e2, flush=True)
                 break
     if bad == 0 or "--bench" in sys.argv:
-        for (M, N, K) in [(8192, 768, 6912), (16384, 256, 2304), (8192, 8192, 8192)]:
+        bn = int(os.environ.get("MDM_BENCH_BN", "256"))
+        for (M, N, K) in [(8192, 768, 6912), (16384, 256, 2304), (8192, 8192, 8192), (16384, 3072, 768)]:
             try:
-                ms, tf, msr, tfr = bench_one(M, N, K)
+                ms, tf, msr, tfr = bench_one(M, N, K, bn=bn)
                 print(f"BENCH {M}x{N}x{K}: ours {ms:.3f} ms {tf:.0f} TFLOP/s | cuBLAS {msr:.3f} ms {tfr:.0f} TFLOP/s",
                       flush=True)
             except Exception as e:
