@@ -603,7 +603,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     stats[row * 2 + 1] = rstd;
   }
   for (int i = threadIdx.x; i < D; i += blockDim.x)
-    y16[row * D + i] = __float2half_rn((xr[i] - mean) * rstd * w[i] + b[i]);
+    y16[row * D + i] = __float2half_rn(w != nullptr ? (xr[i] - mean) * rstd * w[i] + b[i] : (xr[i] - mean) * rstd);
 }
 
 constexpr int LN_ROWS = 16;
@@ -621,7 +621,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     aw[j] = 0.f;
     abias[j] = 0.f;
     const int i = threadIdx.x + j * 256;
-    wv[j] = i < D ? w[i] : 0.f;
+    wv[j] = i < D ? (w != nullptr ? w[i] : 1.f) : 0.f;
   }
   for (int rr = 0; rr < LN_ROWS; ++rr) {
     const long long row = r0 + rr;
@@ -656,6 +656,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       }
     }
   }
+  if (dw == nullptr) return;
   const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
 #pragma unroll
   for (int j = 0; j < LN_COLS; ++j) {
@@ -665,6 +666,50 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       atomicAdd(db + i, inv * abias[j]);
     }
   }
+}
+
+// ---- LayerNorm affine folded into the following Linear (cross-attention kv_cond, unet.py:263-264,304):
+//   kv = Linear(LN(x)) = xhat (W diag(w))^T + (W b + bias)
+__global__ void fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ w, __half* __restrict__ out,
+                                      long long rows, int D) {
+  const long long total = rows * D;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) out[i] = __float2half_rn(W[i] * w[i % D]);
+}
+__global__ void fold_ln_bias_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ bias,
+                                    float* __restrict__ out, int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int j = lane; j < D; j += 32) s += W[static_cast<long long>(row) * D + j] * b[j];
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s + bias[row];
+}
+// gradients back through the fold. dWf: fp32 [rows][D] gradient of the folded weight (already unscaled),
+// dbf: [rows] gradient of the folded bias (unscaled).
+//   dW[i][j] += dWf[i][j] w[j] + dbf[i] b[j];  dw[j] += sum_i dWf[i][j] W[i][j];  db[j] += sum_i dbf[i] W[i][j]
+__global__ void unfold_ln_grads_kernel(const float* __restrict__ dWf, const float* __restrict__ dbf,
+                                       const float* __restrict__ W, const float* __restrict__ w,
+                                       const float* __restrict__ b, float* __restrict__ dW,
+                                       float* __restrict__ dw, float* __restrict__ db, int rows, int D) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const int r0 = blockIdx.y * 64;
+  const int r1 = min(rows, r0 + 64);
+  const float wj = w[j], bj = b[j];
+  float a = 0.f, c = 0.f;
+  for (int i = r0; i < r1; ++i) {
+    const long long o = static_cast<long long>(i) * D + j;
+    const float g = dWf[o];
+    const float Wij = W[o];
+    if (dW != nullptr) dW[o] += g * wj + dbf[i] * bj;
+    a += g * Wij;
+    c += dbf[i] * Wij;
+  }
+  if (dw != nullptr) atomicAdd(dw + j, a);
+  if (db != nullptr) atomicAdd(db + j, c);
 }
 
 // ------------------------------------------------------------------ embeddings / activations
@@ -1103,6 +1148,21 @@ void layernorm_bwd(const float* x, const float* w, const float* stats, const flo
                    float* dw, float* db, const float* inv_scale, long long rows, int D, cudaStream_t st) {
   layernorm_bwd_kernel<<<static_cast<unsigned>(cdiv(rows, LN_ROWS)), 256, 0, st>>>(x, w, stats, dy, dx, acc_dx, dw,
                                                                                  db, inv_scale, rows, D);
+  MDM_LAUNCHED();
+}
+
+void fold_ln_weight(const float* W, const float* w, __half* out, long long rows, int D, cudaStream_t st) {
+  fold_ln_weight_kernel<<<grid_for(rows * D), 256, 0, st>>>(W, w, out, rows, D);
+  MDM_LAUNCHED();
+}
+void fold_ln_bias(const float* W, const float* b, const float* bias, float* out, int rows, int D, cudaStream_t st) {
+  fold_ln_bias_kernel<<<static_cast<unsigned>(cdiv(rows, 8)), 256, 0, st>>>(W, b, bias, out, rows, D);
+  MDM_LAUNCHED();
+}
+void unfold_ln_grads(const float* dWf, const float* dbf, const float* W, const float* w, const float* b, float* dW,
+                     float* dw, float* db, int rows, int D, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(cdiv(D, 256)), static_cast<unsigned>(cdiv(rows, 64)));
+  unfold_ln_grads_kernel<<<grid, 256, 0, st>>>(dWf, dbf, W, w, b, dW, dw, db, rows, D);
   MDM_LAUNCHED();
 }
 

@@ -76,6 +76,12 @@ void layernorm_bwd(const float* x, const float* w, const float* stats, const flo
                    int acc_dx, float* dw, float* db, const float* inv_scale, long long rows, int D,
                    cudaStream_t st);
 
+// LayerNorm affine folded into the Linear that follows it (w, b may be null in layernorm_fwd/bwd: plain xhat)
+void fold_ln_weight(const float* W, const float* w, __half* out, long long rows, int D, cudaStream_t st);
+void fold_ln_bias(const float* W, const float* b, const float* bias, float* out, int rows, int D, cudaStream_t st);
+void unfold_ln_grads(const float* dWf, const float* dbf, const float* W, const float* w, const float* b, float* dW,
+                     float* dw, float* db, int rows, int D, cudaStream_t st);
+
 // ---- embeddings / small elementwise
 // e16[b][0:half]=sin(v*w_i), [half:2half]=cos(v*w_i); w = the reference's t_emb buffer
 // exp(-ln(1e4) i/half) (unet.py:600-603,834-836), bound from the host so it is bit-identical.

@@ -33,6 +33,7 @@ struct AttnSpec {
   std::string pre;
   int C;
   bool cond, ffn;
+  float* kv_bias_fold = nullptr;  // W b_ln + bias of kv_cond with the LayerNorm affine folded in (persistent)
 };
 struct BlockSpec {
   std::string pre;
@@ -81,6 +82,10 @@ struct Net {
     bool dcond_init = false;
     float* y32 = nullptr;
     __half* y16 = nullptr;
+    __half* xhat16 = nullptr;  // LayerNorm(cond) without affine, shared by every cross-attention block
+    float* lnstats = nullptr;  // (B*S, 2) mean, rstd
+    float* dxhat = nullptr;    // gradient w.r.t. xhat, accumulated over the blocks
+    bool dxhat_init = false;
     float* cemb = nullptr;  // (B, td)
     float* dcemb = nullptr;
     bool dcemb_init = false;
@@ -154,7 +159,7 @@ struct Net {
     if (a.cond) {
       add_param(a.pre + ".norm_cond.weight", {cfg.cond_dim}, 0);
       add_param(a.pre + ".norm_cond.bias", {cfg.cond_dim}, 0);
-      add_param(a.pre + ".kv_cond.weight", {2 * C, cfg.cond_dim}, 1);
+      add_param(a.pre + ".kv_cond.weight", {2 * C, cfg.cond_dim}, 5);  // packed with norm_cond folded in
       add_param(a.pre + ".kv_cond.bias", {2 * C}, 0);
     }
     add_param(a.pre + ".proj_out.weight", {C, C, 1, 1}, 1);
@@ -309,7 +314,7 @@ struct Net {
     for (auto& p : plist) {
       if (p.pack == 0) continue;
       MDM_CHECK(p.w != nullptr, ("parameter not bound: " + p.name).c_str());
-      if (p.pack == 4) continue;  // handled per level below
+      if (p.pack == 4 || p.pack == 5) continue;  // handled per level / per attention block below
       if (p.w16 == nullptr) {
         size_t n = static_cast<size_t>(p.numel);
         if (p.pack == 3) n = static_cast<size_t>(p.shape[0]) * 32;
@@ -334,6 +339,23 @@ struct Net {
       for (auto& b : L.down) pack_block(b);
       for (auto& b : L.mid) pack_block(b);
       for (auto& b : L.up) pack_block(b);
+    }
+    for (auto& L : levels) {
+      auto fold_block = [&](BlockSpec& b) {
+        for (auto& a : b.attn) {
+          if (!a.cond) continue;
+          Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
+          Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
+          const int rows = 2 * a.C, D = cfg.cond_dim;
+          if (kw.w16 == nullptr) kw.w16 = static_cast<__half*>(persist(sizeof(__half) * static_cast<size_t>(rows) * D));
+          if (a.kv_bias_fold == nullptr) a.kv_bias_fold = static_cast<float*>(persist(sizeof(float) * rows));
+          fold_ln_weight(kw.w, lw.w, kw.w16, rows, D, st);
+          fold_ln_bias(kw.w, lb.w, kb.w, a.kv_bias_fold, rows, D, st);
+        }
+      };
+      for (auto& b : L.down) fold_block(b);
+      for (auto& b : L.mid) fold_block(b);
+      for (auto& b : L.up) fold_block(b);
     }
     weights_dirty = false;
   }
@@ -632,14 +654,12 @@ struct Net {
       Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
       Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
       const long long crow = static_cast<long long>(B) * S;
-      cn16 = E.alloc<__half>(crow * cd);
-      lnstats = E.alloc<float>(crow * 2);
-      layernorm_fwd(cs.cond32, lw.w, lb.w, cn16, lnstats, crow, cd, E.st);
+      (void)lw; (void)lb; (void)kb;
       kv = E.alloc<__half>(crow * 2 * C);
       Epi e2;
-      e2.bias = kb.w;
+      e2.bias = a.kv_bias_fold;
       e2.out_f16 = kv;
-      E.gemm_nt(cn16, cd, kw.w16, cd, static_cast<int>(crow), 2 * C, cd, e2);
+      E.gemm_nt(cs.xhat16, cd, kw.w16, cd, static_cast<int>(crow), 2 * C, cd, e2);
     }
     if (fused) {
       if (E.training) {
@@ -890,16 +910,30 @@ struct Net {
         Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
         Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
         const long long crow = static_cast<long long>(B) * S;
-        float* dcn = E.alloc<float>(crow * cd);
-        linear_bwd(dkv, 2 * C, static_cast<int>(crow), 2 * C, cd, cn16, cd, kw, &kb, true, dcn, 0);
+        // kv = xhat (W diag(w_ln))^T + (W b_ln + bias): gradients of the folded operands, then unfold
+        float* dbf = E.zeros_f32(2 * C);
+        colsum_f16(dkv, crow, 2 * C, dbf, inv_scale(), E.st);
+        if (kb.g != nullptr) axpy_f32(kb.g, dbf, 1.f, 2 * C, 1, E.st);
+        float* dWf = E.zeros_f32(2ll * C * cd);
+        {
+          Epi e;
+          e.out_f32 = dWf;
+          e.alpha_dev = inv_scale();
+          e.atomic_ok = true;
+          E.gemm_tn(dkv, 2 * C, cs.xhat16, cd, 2 * C, cd, static_cast<int>(crow), e);
+        }
+        unfold_ln_grads(dWf, dbf, kw.w, lw.w, lb.w, kw.g, lw.g, lb.g, 2 * C, cd, E.st);
+        E.pool.release(dWf);
+        E.pool.release(dbf);
+        if (cs.dxhat == nullptr) cs.dxhat = E.alloc<float>(crow * cd);
+        {
+          Epi e;
+          e.out_f32 = cs.dxhat;
+          if (cs.dxhat_init) e.residual = cs.dxhat;
+          E.gemm_nn(dkv, 2 * C, kw.w16, cd, static_cast<int>(crow), cd, 2 * C, e);
+        }
+        cs.dxhat_init = true;
         E.pool.release(dkv);
-        if (cs.dcond == nullptr) cs.dcond = E.alloc<float>(crow * cd);
-        float* dlw = lw.g != nullptr ? lw.g : E.zeros_f32(cd);
-        float* dlb = lb.g != nullptr ? lb.g : E.zeros_f32(cd);
-        layernorm_bwd(cs.cond32, lw.w, lnstats, dcn, cs.dcond, cs.dcond_init ? 1 : 0, dlw, dlb, inv_scale(), crow, cd,
-                      E.st);
-        cs.dcond_init = true;
-        E.pool.release(dcn);
       }
       // qkv conv + norm
       float* dn32 = E.alloc<float>(rows * C);
@@ -1117,6 +1151,11 @@ struct Net {
     } else {
       cs.cond32 = const_cast<float*>(io->lm);
     }
+    {  // LayerNorm(cond) without its affine part, once per forward (31 blocks share it; unet.py:263,304)
+      cs.xhat16 = E.alloc<__half>(crow * cfg.cond_dim);
+      cs.lnstats = E.alloc<float>(crow * 2);
+      layernorm_fwd(cs.cond32, nullptr, nullptr, cs.xhat16, cs.lnstats, crow, cfg.cond_dim, E.st);
+    }
     if (cfg.has_cond_emb) {
       Param& cw = P(L.pre + "cond_emb.weight");
       cs.y32 = E.alloc<float>(static_cast<long long>(B) * cfg.cond_dim);
@@ -1145,6 +1184,12 @@ struct Net {
         }
         E.pool.release(d16);
         E.pool.release(dy);
+      }
+      if (cs.dxhat_init) {
+        if (cs.dcond == nullptr) cs.dcond = E.alloc<float>(crow * cfg.cond_dim);
+        layernorm_bwd(cs.cond32, nullptr, cs.lnstats, cs.dxhat, cs.dcond, cs.dcond_init ? 1 : 0, nullptr, nullptr, nullptr,
+                      crow, cfg.cond_dim, E.st);
+        cs.dcond_init = true;
       }
       if (cfg.has_lm_proj && cs.dcond != nullptr) {
         Param &w = P(L.pre + "lm_proj.weight"), &b = P(L.pre + "lm_proj.bias");
