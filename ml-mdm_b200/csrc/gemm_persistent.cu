@@ -317,8 +317,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const int colg = n0 + g * 64;
           if (colg < p.N) {
             if (p.out_f32 != nullptr) {
-              tma_store_4d(&tmO32, st32, colg, oc1, oc2, oc3);
-              if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_store_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+              if (p.atomic) {
+                tma_reduce_add_4d(&tmO32, st32, colg, oc1, oc2, oc3);
+                if (colg + 32 < p.N && g * 64 + 32 < p.block_n)
+                  tma_reduce_add_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+              } else {
+                tma_store_4d(&tmO32, st32, colg, oc1, oc2, oc3);
+                if (colg + 32 < p.N && g * 64 + 32 < p.block_n)
+                  tma_store_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+              }
             }
             if (p.out_f16 != nullptr) tma_store_4d(&tmO16, st16, colg, oc1, oc2, oc3);
             if (p.out_act_f16 != nullptr) tma_store_4d(&tmOact, stact, colg, oc1, oc2, oc3);

@@ -319,8 +319,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int colg = n0 + g * 64;
         if (colg < p.N) {
           if (p.out_f32 != nullptr) {
-            tma_store_4d(&tmO32, st32, colg, oc1, oc2, oc3);
-            if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_store_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+            if (p.atomic) {  // split-K / accumulate: reduce-add in the TMA unit
+              tma_reduce_add_4d(&tmO32, st32, colg, oc1, oc2, oc3);
+              if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_reduce_add_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+            } else {
+              tma_store_4d(&tmO32, st32, colg, oc1, oc2, oc3);
+              if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_store_4d(&tmO32, st32 + 16384, colg + 32, oc1, oc2, oc3);
+            }
           }
           if (p.out_f16 != nullptr) tma_store_4d(&tmO16, st16, colg, oc1, oc2, oc3);
           if (p.out_act_f16 != nullptr) tma_store_4d(&tmOact, stact, colg, oc1, oc2, oc3);
@@ -547,14 +552,15 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
       if (ptr == nullptr) return true;
       if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
       if ((p.ldc * esz) % 16 != 0) return false;
-      if (p.kind == GEMM_PLAIN && p.nz1 > 1 && (p.c_z1_stride * esz) % 16 != 0) return false;
-      if (p.kind == GEMM_PLAIN && p.nz2 > 1 && (p.c_z2_stride * esz) % 16 != 0) return false;
+      if (p.kind != GEMM_CONV && p.nz1 > 1 && (p.c_z1_stride * esz) % 16 != 0) return false;
+      if (p.kind != GEMM_CONV && p.nz2 > 1 && (p.c_z2_stride * esz) % 16 != 0) return false;
       return true;
     };
     const bool any_out = p.out_f32 != nullptr || p.out_f16 != nullptr || p.out_act_f16 != nullptr;
     const bool shape_ok = (p.block_n % 64 == 0) || (n_tiles == 1);
-    if (!p.atomic && p.kind != GEMM_CONV_WGRAD && any_out && shape_ok && ok(p.out_f32, 4) && ok(p.out_f16, 2) &&
-        ok(p.out_act_f16, 2) && getenv("MDM_NO_TMA_EPILOGUE") == nullptr) {
+    const bool atomic_ok = !p.atomic || (p.out_f16 == nullptr && p.out_act_f16 == nullptr && p.gelu_grad_src == nullptr);
+    if (atomic_ok && any_out && shape_ok && ok(p.out_f32, 4) && ok(p.out_f16, 2) && ok(p.out_act_f16, 2) &&
+        getenv("MDM_NO_TMA_EPILOGUE") == nullptr) {
       auto mk = [&](void* ptr, int esz, uint32_t box0) {
         TmapSpec o;
         o.ptr = ptr;
