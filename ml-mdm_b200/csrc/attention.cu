@@ -134,6 +134,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int nchunks = (nkeys + TILE - 1) / TILE;
     const float* mk = (cross && p.mask != nullptr) ? p.mask + static_cast<long long>(b) * p.S : nullptr;
     float m2 = -INFINITY, l = 0.f;
+    // Self branch over several chunks: pass 0 finds the row maximum only, pass 1 writes unnormalised
+    // P = 2^(s - m) (one exponential per score), and O is divided by l afterwards.
+    const bool deferred = branch == 0 && nchunks > 1;
     // pass 0: statistics (skipped when a single chunk holds the whole row), pass 1: P and O += P V
     for (int pass = (nchunks > 1 ? 0 : 1); pass < 2; ++pass) {
       const bool with_v = pass == 1;
@@ -163,7 +166,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           ++loads;
         }
         const int key0 = c * TILE;
-        // the whole 128-key row of this chunk in registers (one TMEM round trip)
+        // the whole 128-key row of this chunk in registers (one TMEM round trip), raw scores
         float v[TILE];
 #pragma unroll
         for (int j = 0; j < TILE; j += 32) tmem_ld32_nowait(tS + trow + j, v + j);
@@ -174,38 +177,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int e = 0; e < TILE; ++e) {
             const int key = key0 + e;
             const bool ok = key < nkeys && (mk == nullptr || mk[key] != 0.f);
-            v[e] = ok ? v[e] * p.alpha_log2e : -INFINITY;
+            v[e] = ok ? v[e] : -INFINITY;
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < TILE; ++e) v[e] *= p.alpha_log2e;
         }
-        if (pass == 0 || nchunks == 1) {
+        if (pass == 0 || nchunks == 1) {  // running row maximum (alpha > 0: max commutes with the scaling)
           float cm = -INFINITY;
 #pragma unroll
           for (int e = 0; e < TILE; ++e) cm = fmaxf(cm, v[e]);
-          const float mn = fmaxf(m2, cm);
-          const float mref = mn > -INFINITY ? mn : 0.f;
-          float sum = 0.f;
+          cm *= p.alpha_log2e;
+          if (pass == 0 && !deferred && cm > -INFINITY) {
+            // several cross chunks: the sum is needed before P can be written, so pass 0 carries it too
+            const float mn = fmaxf(m2, cm);
+            float sum = 0.f;
 #pragma unroll
-          for (int e = 0; e < TILE; ++e) sum += exp2f(v[e] - mref);  // exp2(-inf) = 0 for masked keys
-          if (mn > -INFINITY) {
-            l = l * (m2 > -INFINITY ? exp2f(m2 - mn) : 0.f) + sum;
-            m2 = mn;
+            for (int e = 0; e < TILE; ++e) sum += ex2_approx(fmaf(v[e], p.alpha_log2e, -mn));
+            l = l * (m2 > -INFINITY ? ex2_approx(m2 - mn) : 0.f) + sum;
           }
+          m2 = fmaxf(m2, cm);
         }
         if (pass == 0) {
           tc_fence_before();
           __syncthreads();  // everyone is done with S before the next chunk overwrites it
         } else {
-          const float inv_l = l > 0.f ? 1.0f / l : 0.f;
           const float mref = m2 > -INFINITY ? m2 : 0.f;
+          float sum = 0.f;
+#pragma unroll
+          for (int e = 0; e < TILE; ++e) {
+            v[e] = ex2_approx(fmaf(v[e], p.alpha_log2e, -mref));  // 2^-inf = 0 for masked keys
+            sum += v[e];
+          }
+          if (deferred || nchunks == 1) l += sum;
+          // deferred: P stays unnormalised (<= 1) and O is divided by l once after the branch
+          const float pscale = deferred ? 1.f : (l > 0.f ? 1.0f / l : 0.f);
 #pragma unroll
           for (int j = 0; j < TILE; j += 8) {
             __half2 h[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2)
-              h[e >> 1] = __floats2half2_rn(exp2f(v[j + e] - mref) * inv_l, exp2f(v[j + e + 1] - mref) * inv_l);
+            for (int e = 0; e < 8; e += 2) h[e >> 1] = __floats2half2_rn(v[j + e] * pscale, v[j + e + 1] * pscale);
             st_swz_half8(sP, tid, j >> 3, h);
           }
           fence_proxy_async();
@@ -228,18 +236,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       st[0] = m2;
       st[1] = l > 0.f ? 1.0f / l : 0.f;
     }
-    if (branch == 0 && p.oself16 != nullptr) {
-      // self-branch output alone (the backward needs rowsum(dO * O_branch) per branch)
+    if (branch == 0 && (p.oself16 != nullptr || deferred)) {
+      // self-branch output alone (the backward needs rowsum(dO * O_branch) per branch); a deferred
+      // normalisation is applied here and written back so the cross branch accumulates on top of it
       if (tid == 0) umma_commit(&o_bar);
       mbar_wait(&o_bar, 0);
       tc_fence_after();
       {
         const bool valid = q0 + tid < p.T;
-        __half* dst = p.oself16 + (static_cast<long long>(b) * p.T + q0 + tid) * p.C + hd * p.d;
+        const float oscale = deferred ? (l > 0.f ? 1.0f / l : 0.f) : 1.f;
+        __half* dst = p.oself16 != nullptr ? p.oself16 + (static_cast<long long>(b) * p.T + q0 + tid) * p.C + hd * p.d
+                                           : nullptr;
         for (int j = 0; j < p.d; j += 16) {
           float v[16];
           tmem_ld16(tO + trow + j, v);
-          if (!valid) continue;
+          if (deferred) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] *= oscale;
+            tmem_st16(tO + trow + j, v);
+          }
+          if (!valid || dst == nullptr) continue;
           __half2 h[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
@@ -250,6 +266,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             for (int e = 0; e < 16 && j + e < p.d; ++e) dst[j + e] = __float2half_rn(v[e]);
           }
         }
+        if (deferred) tmem_st_wait();
       }
       tc_fence_before();
       __syncthreads();
@@ -315,7 +332,8 @@ __global__ void attn_bwd_prep_kernel(const __half* __restrict__ dO, const __half
 
 __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
-                const __grid_constant__ CUtensorMap tmDO, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
+                const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_bar, qd_bar, mma_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -340,6 +358,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmKV);
     prefetch_tmap(&tmDO);
+    prefetch_tmap(&tmDQ);
     mbar_init(&kv_bar, 1);
     mbar_init(&qd_bar, 1);
     mbar_init(&mma_bar, 1);
@@ -394,6 +413,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int kb = 0; kb < kbk; ++kb)
         for (int k = 0; k < 4; ++k)
           umma_f16(tDP, desc_k(da + kb * KB_BYTES, k), desc_k(va + kb * KB_BYTES, k), id_kk, (kb | k) ? 1u : 0u);
+      // the previous tile's dQ reduction must have read its staging (= the P / dS tiles) before they
+      // are rewritten; the commit below is issued after this wait, so mma_bar orders it for everyone
+      bulk_wait_read();
       umma_commit(&mma_bar);
     }
     qd_phase ^= 1;
@@ -428,7 +450,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             for (int u = 0; u < 2; ++u) {
               const int key = key0 + j0 + j + e + u;
               const bool ok = qok && key < nkeys && (mk == nullptr || mk[key] != 0.f) && inv_l > 0.f;
-              pv[u] = ok ? exp2f(s[j + e + u] * p.alpha_log2e - m2) * inv_l : 0.f;
+              pv[u] = ok ? ex2_approx(fmaf(s[j + e + u], p.alpha_log2e, -m2)) * inv_l : 0.f;
               ds[u] = pv[u] * (dp[j + e + u] - Dq) * p.alpha;
             }
             hp[e >> 1] = __floats2half2_rn(pv[0], pv[1]);
@@ -458,25 +480,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // all MMAs that read Q / dO have retired: fetch the next query tile under the dQ drain
     if (tid == 0 && it + 1 < nq) load_qd((it + 1) * TILE);
     {
-      const int q = q0 + tid;
-      float* dst = p.dq32 + (static_cast<long long>(b) * p.T + q) * p.C + hd * p.d;
+      // dQ tile: TMEM -> 128B-swizzled fp32 staging (the dead P / dS tiles) -> one TMA reduce-add per
+      // 32 columns; rows beyond T and columns beyond d are clipped by the tensor map
+      uint8_t* stg = sP;
+      const uint32_t swz = static_cast<uint32_t>(tid & 7);
       for (int j = 0; j < p.d; j += 16) {
         float v[16];
         tmem_ld16(tS + trow + j, v);
-        if (q < p.T) {
-          if (j + 16 <= p.d) {
+        uint8_t* base = stg + (j >> 5) * KB_BYTES + tid * 128;
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              atomicAdd(reinterpret_cast<float4*>(dst + j + e), make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-          } else {
-            for (int e = 0; e < 16 && j + e < p.d; ++e) atomicAdd(dst + j + e, v[e]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t chunk = static_cast<uint32_t>(((j & 16) >> 2) + e) ^ swz;
+          *reinterpret_cast<float4*>(base + chunk * 16) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
       }
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      for (int g = 0; g * 32 < p.d; ++g) tma_reduce_add_4d(&tmDQ, sP + g * KB_BYTES, g * 32, q0, hd, b);
+      bulk_commit();
+    }
   }
+  if (tid == 0) bulk_wait_all();
   // dK, dV of this key tile
   {
     const int key = key0 + tid;
@@ -567,6 +594,21 @@ void head_map(CUtensorMap* m, const void* ptr, int d, int rows, long long row_st
   MDM_CHECK(r == CUDA_SUCCESS, "attention tensor map encode failed");
 }
 
+// fp32 [B*T][C] viewed per head: (d, rows, heads, batch), box {32, 128, 1, 1}
+void head_map_f32(CUtensorMap* m, const void* ptr, int d, int rows, long long row_stride, int slots, int batch) {
+  EncodeTiledFn fn = encode_fn();
+  MDM_CHECK(fn != nullptr, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(slots),
+                        static_cast<cuuint64_t>(batch)};
+  cuuint64_t str[3] = {static_cast<cuuint64_t>(row_stride) * 4, static_cast<cuuint64_t>(d) * 4,
+                       static_cast<cuuint64_t>(rows) * row_stride * 4};
+  cuuint32_t box[4] = {32, 128, 1, 1}, es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, str, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MDM_CHECK(r == CUDA_SUCCESS, "attention dQ tensor map encode failed");
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host API
@@ -616,7 +658,8 @@ void attention_backward(const __half* qkv, const __half* kv, const float* mask, 
   attn_bwd_prep_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(dO, h16, oself16, Dterm, T, C, heads, d, rows);
   ++g_launch_count;
   MDM_CUDA(cudaMemsetAsync(dq32, 0, sizeof(float) * rows * C, st));
-  alignas(64) CUtensorMap mq, mk, mdo;
+  alignas(64) CUtensorMap mq, mk, mdo, mdq;
+  head_map_f32(&mdq, dq32, d, T, C, heads, B);
   head_map(&mq, qkv, d, T, 3ll * C, 3 * heads, d, B, static_cast<long long>(T) * 3 * C);
   if (kv != nullptr) head_map(&mk, kv, d, S, 2ll * C, 2 * heads, d, B, static_cast<long long>(S) * 2 * C);
   else mk = mq;
@@ -630,7 +673,7 @@ void attention_backward(const __half* qkv, const __half* kv, const float* mask, 
   }
   const int n_self = (T + TILE - 1) / TILE, n_cross = p.S > 0 ? (p.S + TILE - 1) / TILE : 0;
   dim3 grid(n_self + n_cross, heads, B);
-  attn_bwd_kernel<<<grid, AT_THREADS, smem, st>>>(mq, mk, mdo, p);
+  attn_bwd_kernel<<<grid, AT_THREADS, smem, st>>>(mq, mk, mdo, mdq, p);
   ++g_launch_count;
   MDM_CUDA(cudaGetLastError());
   // dQ: fp32 accumulator -> fp16 into the q third of dqkv
