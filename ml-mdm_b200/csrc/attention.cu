@@ -22,6 +22,7 @@ using namespace ptx;
 namespace {
 
 constexpr int AT_THREADS = 128;
+constexpr int BWD_THREADS = 256;  // backward: two warpgroups split every tile by columns
 constexpr int TILE = 128;           // queries per CTA (fwd) / keys per CTA (bwd); key chunk size
 constexpr int KB_BYTES = 128 * 128; // one [128 rows][64 fp16] k-block / slab
 
@@ -62,10 +63,10 @@ __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVv,
                 const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVv,
                 const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_bar, kv_bar[2], s_bar, o_bar;
-  __shared__ uint32_t tmem_base_smem;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // No static shared memory: the dynamic segment starts the CTA's window, 1024-aligned as the swizzled
+  // tiles need, so two CTAs (2 x 112 KB of tiles at d = 64) fit one SM.
+  extern __shared__ __align__(1024) uint8_t attn_fwd_smem[];
+  uint8_t* smem = attn_fwd_smem;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * TILE;
@@ -74,6 +75,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + kbk * KB_BYTES;
   uint8_t* sP = sKV + 2 * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * KB_BYTES);
+  uint64_t& q_bar = bars[0];
+  uint64_t* kv_bar = bars + 1;
+  uint64_t& s_bar = bars[3];
+  uint64_t& o_bar = bars[4];
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 5);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   if (tid == 0) {
     prefetch_tmap(&tmQKV);
@@ -104,13 +112,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t idesc_pv = make_idesc_f16(128, (p.d + 15) / 16 * 16, 0, 1);
   uint32_t kv_phase[2] = {0, 0};
   uint32_t s_phase = 0;
-  int loads = 0;  // chunk loads issued so far (stage = loads & 1)
   bool o_started = false;
 
-  auto issue_load = [&](bool cross, int chunk, bool with_v) {
-    const int st = loads & 1;
+  // K / V chunk loads form one queue across passes and branches (two stages), so the first chunk of
+  // the next pass or branch is already in flight while the current one finishes.
+  const int nself = (p.T + TILE - 1) / TILE;
+  const int ncross = p.S > 0 ? (p.S + TILE - 1) / TILE : 0;
+  const int self_p0 = nself > 1 ? nself : 0;   // statistics-pass items of the self branch
+  const int items_self = self_p0 + nself;
+  const int cross_p0 = ncross > 1 ? ncross : 0;
+  const int n_items = items_self + cross_p0 + ncross;
+  auto issue_item = [&](int i) {
+    const bool cross = i >= items_self;
+    const int k = cross ? i - items_self : i;
+    const int p0 = cross ? cross_p0 : self_p0;
+    const bool with_v = k >= p0;
+    const int key0 = (with_v ? k - p0 : k) * TILE;
+    const int st = i & 1;
     uint8_t* dst = sKV + st * stage_bytes;
-    const int key0 = chunk * TILE;
     mbar_expect_tx(&kv_bar[st], (with_v ? 2 : 1) * kbk * KB_BYTES);
     for (int kb = 0; kb < kbk; ++kb) {
       if (!cross) tma_load_4d(dst + kb * KB_BYTES, &tmQKV, &kv_bar[st], kb * 64, key0, p.heads + hd, b);
@@ -123,6 +142,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   };
+  int item = 0;  // queue position of the chunk being consumed
+  if (tid == 0 && n_items > 0) issue_item(0);
 
   if (tid == 0) mbar_wait(&q_bar, 0);
   __syncthreads();
@@ -139,12 +160,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool deferred = branch == 0 && nchunks > 1;
     // pass 0: statistics (skipped when a single chunk holds the whole row), pass 1: P and O += P V
     for (int pass = (nchunks > 1 ? 0 : 1); pass < 2; ++pass) {
-      const bool with_v = pass == 1;
-      int consumed_base = loads;
-      if (tid == 0) issue_load(cross, 0, with_v);
-      ++loads;
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = (consumed_base + c) & 1;
+      for (int c = 0; c < nchunks; ++c, ++item) {
+        const int st = item & 1;
         uint8_t* sK = sKV + st * stage_bytes;
         uint8_t* sV = sK + kbk * KB_BYTES;
         if (tid == 0) {
@@ -160,11 +177,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(&s_bar, s_phase);
         s_phase ^= 1;
         tc_fence_after();
-        // the previous chunk's PV has retired (commit covers all earlier MMAs): its stage is free
-        if (c + 1 < nchunks) {
-          if (tid == 0) issue_load(cross, c + 1, with_v);
-          ++loads;
-        }
+        // the previous item's MMAs have retired (the commit covers all earlier ones): its stage is free
+        if (tid == 0 && item + 1 < n_items) issue_item(item + 1);
         const int key0 = c * TILE;
         // the whole 128-key row of this chunk in registers (one TMEM round trip), raw scores
         float v[TILE];
@@ -330,7 +344,7 @@ __global__ void attn_bwd_prep_kernel(const __half* __restrict__ dO, const __half
   }
 }
 
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                 const AttnParams p) {
@@ -338,7 +352,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __shared__ __align__(8) uint64_t kv_bar, qd_bar, mma_bar;
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 8 warps: warp w owns TMEM lanes 32 (w % 4) .. +31 (= tile rows) and column half w / 4
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int lrow = tid & 127, wg = tid >> 7;
   const int hd = blockIdx.y, b = blockIdx.z;
   const int n_self = (p.T + TILE - 1) / TILE;
   const bool cross = static_cast<int>(blockIdx.x) >= n_self;
@@ -370,7 +386,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 384;
-  const uint32_t trow = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t trow = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const int dN = (p.d + 15) / 16 * 16;
   const uint32_t id_kk = make_idesc_f16(128, 128, 0, 0);   // S, dP
   const uint32_t id_tt = make_idesc_f16(128, dN, 1, 1);    // dV, dK (A = P^T / dS^T, B = dO / Q rows)
@@ -422,9 +438,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_wait(&mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    // thread = query row
+    // thread = query row x 64-key half
     {
-      const int q = q0 + tid;
+      const int q = q0 + lrow;
       const bool qok = q < p.T;
       float m2 = 0.f, inv_l = 0.f, Dq = 0.f;
       if (qok) {
@@ -433,32 +449,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         inv_l = st[1];
         Dq = p.Dterm[((static_cast<long long>(b) * p.heads + hd) * 2 + branch) * p.T + q];
       }
-      for (int j0 = 0; j0 < TILE; j0 += 64) {
-        float s[64], dp[64];
-        tmem_ld32_nowait(tS + trow + j0, s);
-        tmem_ld32_nowait(tS + trow + j0 + 32, s + 32);
-        tmem_ld32_nowait(tDP + trow + j0, dp);
-        tmem_ld32_nowait(tDP + trow + j0 + 32, dp + 32);
-        tmem_ld_wait();
+      if (!(inv_l > 0.f)) {  // row outside the tile or fully masked: P = 0 without inf arithmetic
+        inv_l = 0.f;
+        m2 = 0.f;
+      }
+      const float nDq = -Dq * p.alpha;
+      const int j0 = wg * 64;
+      float s[64], dp[64];
+      tmem_ld32_nowait(tS + trow + j0, s);
+      tmem_ld32_nowait(tS + trow + j0 + 32, s + 32);
+      tmem_ld32_nowait(tDP + trow + j0, dp);
+      tmem_ld32_nowait(tDP + trow + j0 + 32, dp + 32);
+      tmem_ld_wait();
+      const bool plain = mk == nullptr && key0 + TILE <= nkeys;  // uniform: no per-key predicate needed
 #pragma unroll
-        for (int j = 0; j < 64; j += 8) {
-          __half2 hp[4], hs[4];
+      for (int j = 0; j < 64; j += 8) {
+        __half2 hp[4], hs[4];
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float pv[2], ds[2];
+        for (int e = 0; e < 8; e += 2) {
+          float pv[2], ds[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < 2; ++u) {
+            float pe = ex2_approx(fmaf(s[j + e + u], p.alpha_log2e, -m2)) * inv_l;
+            if (!plain) {
               const int key = key0 + j0 + j + e + u;
-              const bool ok = qok && key < nkeys && (mk == nullptr || mk[key] != 0.f) && inv_l > 0.f;
-              pv[u] = ok ? ex2_approx(fmaf(s[j + e + u], p.alpha_log2e, -m2)) * inv_l : 0.f;
-              ds[u] = pv[u] * (dp[j + e + u] - Dq) * p.alpha;
+              const bool ok = key < nkeys && (mk == nullptr || mk[key] != 0.f);
+              pe = ok ? pe : 0.f;
             }
-            hp[e >> 1] = __floats2half2_rn(pv[0], pv[1]);
-            hs[e >> 1] = __floats2half2_rn(ds[0], ds[1]);
+            pv[u] = pe;
+            ds[u] = pe * fmaf(dp[j + e + u], p.alpha, nDq);  // P (dP - D) / sqrt(d)
           }
-          st_swz_half8(sP, tid, (j0 + j) >> 3, hp);
-          st_swz_half8(sDS, tid, (j0 + j) >> 3, hs);
+          hp[e >> 1] = __floats2half2_rn(pv[0], pv[1]);
+          hs[e >> 1] = __floats2half2_rn(ds[0], ds[1]);
         }
+        st_swz_half8(sP, lrow, (j0 + j) >> 3, hp);
+        st_swz_half8(sDS, lrow, (j0 + j) >> 3, hs);
       }
     }
     fence_proxy_async();
@@ -483,11 +508,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // dQ tile: TMEM -> 128B-swizzled fp32 staging (the dead P / dS tiles) -> one TMA reduce-add per
       // 32 columns; rows beyond T and columns beyond d are clipped by the tensor map
       uint8_t* stg = sP;
-      const uint32_t swz = static_cast<uint32_t>(tid & 7);
-      for (int j = 0; j < p.d; j += 16) {
+      const uint32_t swz = static_cast<uint32_t>(lrow & 7);
+      for (int j = wg * 16; j < p.d; j += 32) {
         float v[16];
         tmem_ld16(tS + trow + j, v);
-        uint8_t* base = stg + (j >> 5) * KB_BYTES + tid * 128;
+        uint8_t* base = stg + (j >> 5) * KB_BYTES + lrow * 128;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t chunk = static_cast<uint32_t>(((j & 16) >> 2) + e) ^ swz;
@@ -506,7 +531,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (tid == 0) bulk_wait_all();
   // dK, dV of this key tile
   {
-    const int key = key0 + tid;
+    const int key = key0 + lrow;
     const bool ok = key < nkeys;
     __half *dk, *dv;
     if (!cross) {
@@ -518,7 +543,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       dk = base;
       dv = base + p.C;
     }
-    for (int j = 0; j < p.d; j += 16) {
+    for (int j = wg * 16; j < p.d; j += 32) {
       float a[16], c[16];
       tmem_ld16(tDK + trow + j, a);
       tmem_ld16(tDV + trow + j, c);
@@ -630,7 +655,7 @@ void attention_forward(const __half* qkv, const __half* kv, const float* mask, i
   else mk = mq;
   mkv = mk;
   const int kbk = p.kblocks;
-  const size_t smem = static_cast<size_t>(kbk) * KB_BYTES + 2 * (2 * kbk * KB_BYTES) + 2 * KB_BYTES + 1024;
+  const size_t smem = static_cast<size_t>(kbk) * KB_BYTES + 2 * (2 * kbk * KB_BYTES) + 2 * KB_BYTES + 64;
   static bool attr = false;
   if (!attr) {
     MDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -673,7 +698,7 @@ void attention_backward(const __half* qkv, const __half* kv, const float* mask, 
   }
   const int n_self = (T + TILE - 1) / TILE, n_cross = p.S > 0 ? (p.S + TILE - 1) / TILE : 0;
   dim3 grid(n_self + n_cross, heads, B);
-  attn_bwd_kernel<<<grid, AT_THREADS, smem, st>>>(mq, mk, mdo, mdq, p);
+  attn_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(mq, mk, mdo, mdq, p);
   ++g_launch_count;
   MDM_CUDA(cudaGetLastError());
   // dQ: fp32 accumulator -> fp16 into the q third of dqkv
