@@ -4,7 +4,8 @@
 //   one CTA per SM, looping over output tiles (m fastest, so concurrently running CTAs share B tiles in L2)
 //   warp 0      : TMA producer (one lane)          -- smem ring of 64-deep K stages, full/empty mbarriers
 //   warp 1      : tcgen05.mma issuer (one lane)    -- two 256-column fp32 accumulators in TMEM
-//   warps 2..9  : epilogue (256 threads)           -- drain accumulator t while the MMA warp fills t+1
+//   warps 2..17 : epilogue (512 threads)           -- drain accumulator t while the MMA warp fills t+1;
+//                 warp w owns TMEM lanes 32 (w % 4).. and the 16-column quarter (w - 2) / 4 of each 64-column group
 // The epilogue stages 64-column groups through 128B-swizzled shared memory and writes them with TMA stores.
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,11 +24,9 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int SLAB_BYTES = 64 * 64 * 2;
 constexpr int MAX_STAGES = 8;
-constexpr int P_THREADS = 320;      // 10 warps
-constexpr int EPI_THREADS = 256;    // warps 2..9
-constexpr int STAGING_BYTES = 65536;  // f32 (2 x 16 KB) + f16 (16 KB) + act (16 KB)
+constexpr int P_THREADS = 576;      // 18 warps: producer, MMA issuer, 16 epilogue warps
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 struct TileCoord {
   int m_tile, n_tile, z1, z2;
@@ -45,7 +44,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_bias[256];
+  __shared__ __align__(16) float s_bias[256];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* staging = smem;                  // epilogue staging first (fixed size), pipeline stages after it
@@ -66,7 +65,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], 16);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -182,9 +181,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   } else {
     // =========================== epilogue warps ===========================
-    const int et = threadIdx.x - 64;                 // 0..255
+    const int et = threadIdx.x - 64;                 // 0..511
     const int r = ((warp & 3) << 5) + lane;          // TMEM lane == tile row (warp w may touch lanes 32*(w%4)..)
-    const int half_id = (warp - 2) >> 2;             // warps 2..5 -> 0, 6..9 -> 1
+    const int quarter = (warp - 2) >> 2;             // 16-column chunk of each 64-column group
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     uint8_t* st32 = staging;
     uint8_t* st16 = staging + (p.out_f32 != nullptr ? 32768 : 0);
@@ -220,62 +219,115 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                   static_cast<long long>(c.z2) * p.c_z2_stride;
         oc1 = m0; oc2 = c.z1; oc3 = c.z2;
       }
+      // GELU' operand of the first column group: requested now, consumed after the accumulator wait
+      uint4 nsrc[2];
+      bool nsrc_ok = false;
+      auto request = [&](int g) {
+        const int cidx = g * 64 + quarter * 16;
+        const int col0 = n0 + cidx;
+        const long long off0 = row_off + col0;
+        const bool inb = cidx < p.block_n && valid && col0 + 16 <= p.N;
+        nsrc_ok = p.gelu_grad_src != nullptr && inb && ((off0 & 7) == 0);
+        if (nsrc_ok) {
+          const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.gelu_grad_src) + off0);
+          nsrc[0] = __ldg(gp);
+          nsrc[1] = __ldg(gp + 1);
+        }
+        if (p.residual != nullptr && inb) prefetch_l2(p.residual + off0);
+      };
+      request(0);
       // bias tile (previous tile's readers are past the group barriers below)
       epi_bar_sync();
-      s_bias[et] = (p.bias != nullptr && et < p.block_n && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+      if (et < 256) s_bias[et] = (p.bias != nullptr && et < p.block_n && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
       epi_bar_sync();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       for (int g = 0; g < ngroups; ++g) {
-        if (stores_pending) {  // staging buffer still being read by the previous group's TMA stores
+        // ---- phase A (registers only): TMEM -> alpha/bias/residual/GELU' -> packed results. The global
+        // operands are requested first so their latency hides under the TMEM load.
+        const int cidx = g * 64 + quarter * 16;
+        const int col0 = n0 + cidx;
+        const bool live = cidx < p.block_n;  // warp-uniform
+        const long long off0 = row_off + col0;
+        const bool inb = live && valid && col0 + 16 <= p.N;
+        const bool res_fast = p.residual != nullptr && inb && ((off0 & 3) == 0);
+        const bool src_fast = nsrc_ok;
+        float v[16];
+        __half2 h16[8], hact[8];
+        float4 rres[4];
+        uint4 rsrc[2];
+        rsrc[0] = nsrc[0];
+        rsrc[1] = nsrc[1];
+        if (res_fast) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + off0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rres[q] = __ldg(rp + q);
+        }
+        if (g + 1 < ngroups) request(g + 1);  // next group's operands travel while this one is processed
+        if (live) {
+          tmem_ld16(taddr_row + static_cast<uint32_t>(cidx), v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(&s_bias[cidx + 4 * q]);
+            v[4 * q + 0] = fmaf(v[4 * q + 0], alpha, bq.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], alpha, bq.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], alpha, bq.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], alpha, bq.w);
+          }
+          if (res_fast) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v[4 * q + 0] += rres[q].x; v[4 * q + 1] += rres[q].y;
+              v[4 * q + 2] += rres[q].z; v[4 * q + 3] += rres[q].w;
+            }
+          } else if (p.residual != nullptr && valid && col0 < p.N) {
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.residual + off0 + j);
+          }
+          if (src_fast) {
+            const __half2* h0 = reinterpret_cast<const __half2*>(&rsrc[0]);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&rsrc[1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 a = __half22float2(h0[q]), b2 = __half22float2(h1[q]);
+              v[2 * q] *= gelu_grad(a.x);
+              v[2 * q + 1] *= gelu_grad(a.y);
+              v[8 + 2 * q] *= gelu_grad(b2.x);
+              v[8 + 2 * q + 1] *= gelu_grad(b2.y);
+            }
+          } else if (p.gelu_grad_src != nullptr && valid && col0 < p.N) {
+            const __half* gp = reinterpret_cast<const __half*>(p.gelu_grad_src) + off0;
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) v[j] *= gelu_grad(__half2float(gp[j]));
+          }
+          if (p.out_f16 != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h16[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          }
+          if (p.out_act_f16 != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float a0 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q]) : v[2 * q];
+              const float a1 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q + 1]) : v[2 * q + 1];
+              hact[q] = __floats2half2_rn(a0, a1);
+            }
+          }
+        }
+        if (g == ngroups - 1) {
+          // last TMEM read of this tile is done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        // ---- the staging buffer may still be read by the previous group's TMA stores
+        if (stores_pending) {
           if (et == 0) bulk_wait_read();
           epi_bar_sync();
         }
-#pragma unroll 1
-        for (int ci = 0; ci < 2; ++ci) {
-          const int cc = half_id * 2 + ci;
-          const int cidx = g * 64 + cc * 16;
-          if (cidx >= p.block_n) break;  // warp-uniform
-          float v[16];
-          tmem_ld16(taddr_row + static_cast<uint32_t>(cidx), v);
-          const int col0 = n0 + cidx;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[j] * alpha + s_bias[cidx + j];
-          if (p.residual != nullptr && valid && col0 < p.N) {
-            const long long off0 = row_off + col0;
-            if (col0 + 16 <= p.N && ((off0 & 3) == 0)) {
-              const float4* rp = reinterpret_cast<const float4*>(p.residual + off0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 t = __ldg(rp + q);
-                v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-              }
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.N) v[j] += __ldg(p.residual + off0 + j);
-            }
-          }
-          if (p.gelu_grad_src != nullptr && valid && col0 < p.N) {
-            const __half* gp = reinterpret_cast<const __half*>(p.gelu_grad_src) + row_off + col0;
-            if (col0 + 16 <= p.N && (((row_off + col0) & 7) == 0)) {
-              const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(gp));
-              const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
-              const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
-              const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 a = __half22float2(h0[q]), b2 = __half22float2(h1[q]);
-                v[2 * q] *= gelu_grad(a.x);
-                v[2 * q + 1] *= gelu_grad(a.y);
-                v[8 + 2 * q] *= gelu_grad(b2.x);
-                v[8 + 2 * q + 1] *= gelu_grad(b2.y);
-              }
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.N) v[j] *= gelu_grad(__half2float(gp[j]));
-            }
-          }
+        // ---- phase B: registers -> 128B-swizzled staging tiles
+        if (live) {
+          const int cc = quarter;
           if (p.out_f32 != nullptr) {
             uint8_t* base = st32 + (cc >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -286,30 +338,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           if (p.out_f16 != nullptr) {
             uint8_t* base = st16 + r * 128;
-            __half2 h[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[0]);
-            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[4]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h16[0]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h16[4]);
           }
           if (p.out_act_f16 != nullptr) {
             uint8_t* base = stact + r * 128;
-            __half2 h[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float a0 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q]) : v[2 * q];
-              const float a1 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q + 1]) : v[2 * q + 1];
-              h[q] = __floats2half2_rn(a0, a1);
-            }
-            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[0]);
-            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h[4]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&hact[0]);
+            *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&hact[4]);
           }
-        }
-        if (g == ngroups - 1) {
-          // last TMEM read of this tile is done: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         fence_proxy_async();
         epi_bar_sync();

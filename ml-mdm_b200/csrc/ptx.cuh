@@ -182,6 +182,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // 2^x on the SFU (one MUFU.EX2; 2^-inf = 0, results below 2^-126 flush to 0)
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -258,6 +258,51 @@ def bench_one(M, N, K, iters=20, bn=256):
     return ms, fl / ms / 1e9, ms_ref, fl / ms_ref / 1e9
 
 
+def bench_epi(M, N, K, bn, mode, iters=20, b_mn=False):
+    """Epilogue variants of one plain GEMM: f16 | f32 | gelu (bias, pre-activation + GELU copies) | ggrad."""
+    A = torch.randn(M, K, device=DEV).to(torch.float16)
+    sa = _lib.tmap(A.data_ptr(), (K, M, 1, 1), (1, K, K * M, K * M), (64, 128, 1, 1))
+    if b_mn:
+        B = torch.randn(K, N, device=DEV).to(torch.float16)
+        sb = _lib.tmap(B.data_ptr(), (N, K, 1, 1), (1, N, N * K, N * K), (64, 64, 1, 1))
+    else:
+        B = torch.randn(N, K, device=DEV).to(torch.float16)
+        sb = _lib.tmap(B.data_ptr(), (K, N, 1, 1), (1, K, K * N, K * N), (64, bn, 1, 1))
+    out = torch.zeros(M, N, device=DEV, dtype=torch.float16)
+    out2 = torch.zeros(M, N, device=DEV, dtype=torch.float16)
+    out32 = torch.zeros(M, N, device=DEV, dtype=torch.float32) if mode == "f32" else None
+    bias = torch.randn(N, device=DEV)
+    src = torch.randn(M, N, device=DEV).to(torch.float16)
+    p = _lib.GemmParams()
+    p.kind = 0
+    p.M, p.N, p.K = M, N, K
+    p.block_n = bn
+    p.num_kblocks = K // 64
+    p.alpha = 1.0
+    p.ldc = N
+    if mode == "f32":
+        p.out_f32 = out32.data_ptr()
+    else:
+        p.out_f16 = out.data_ptr()
+    if mode == "gelu":
+        p.bias = bias.data_ptr()
+        p.out_act_f16 = out2.data_ptr()
+        p.act = 1
+    if mode == "ggrad":
+        p.gelu_grad_src = src.data_ptr()
+    for _ in range(3):
+        _lib.gemm_raw(sa, sb, 0, 1 if b_mn else 0, p, _stream())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        _lib.gemm_raw(sa, sb, 0, 1 if b_mn else 0, p, _stream())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return ms, 2.0 * M * N * K / ms / 1e9
+
+
 def ncu_target():
     """Three launches of the largest 64x64-level conv of the cc12m_64x64 U-Net at batch 64
     (3x3, 256->256 @ 64x64: M = 262144 pixels, N = 256, K = 2304) for an `ncu --set full` capture."""
@@ -268,6 +313,13 @@ def ncu_target():
 if __name__ == "__main__":
     if "--ncu-conv" in sys.argv:
         ncu_target()
+        sys.exit(0)
+    if "--bench-epi" in sys.argv:
+        for (M, N, K) in [(16384, 3072, 768), (16384, 768, 3072), (16384, 768, 768), (65536, 2048, 512)]:
+            for mode, b_mn in (("f16", False), ("f32", False), ("gelu", False), ("ggrad", True), ("f16", True)):
+                for bn in (256, 192, 128):
+                    ms, tf = bench_epi(M, N, K, bn, mode, b_mn=b_mn)
+                    print(f"EPI {M}x{N}x{K} {mode:5s} b_mn={int(b_mn)} bn={bn}: {ms*1e3:7.1f} us {tf:6.0f} TFLOP/s", flush=True)
         sys.exit(0)
     bad = 0
     for name, fn in CASES:
