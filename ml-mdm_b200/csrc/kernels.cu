@@ -60,7 +60,19 @@ __device__ __forceinline__ float4 ld_dy(const void* dy, long long off) {
   return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(dy) + off));
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid on the SFU: rcp(1 + 2^(-x log2 e)); saturates cleanly (2^+inf -> rcp(inf) = 0, 2^-inf -> 1)
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+// pixels handled per loop trip of the GroupNorm streaming kernels: all their loads are issued before the
+// first use, which is what keeps enough bytes in flight at the 25-40 % occupancy these kernels run at
+template <int NL>
+struct PixUnroll {
+  static constexpr int U = NL == 1 ? 4 : (NL == 2 ? 2 : 1);
+};
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float silu_grad(float x) {
   const float s = sigmoidf_(x);
@@ -120,13 +132,24 @@ __global__ void __launch_bounds__(TPB) gn_stats_kernel(Src2 x, int HW, int G, fl
     q[j] = make_float4(0, 0, 0, 0);
   }
   if (m.active) {
-    for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
-      const long long pix = static_cast<long long>(n) * HW + p;
+    constexpr int U = PixUnroll<NL>::U;
+    for (int p = p_begin + m.sub; p < p_end; p += U * m.ppi) {
+      float4 vv[U][NL];
 #pragma unroll
-      for (int j = 0; j < NL; ++j) {
-        const int l = m.t_lane + j * m.stride;
-        if (l < m.lanes) {
-          const float4 v = ld_src(x, pix, 4 * l);
+      for (int u = 0; u < U; ++u) {
+        const int pu = p + u * m.ppi;
+        const long long pix = static_cast<long long>(n) * HW + pu;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          const int l = m.t_lane + j * m.stride;
+          vv[u][j] = (l < m.lanes && pu < p_end) ? ld_src(x, pix, 4 * l) : make_float4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          const float4 v = vv[u][j];  // zeros where out of range
           s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
           q[j].x += v.x * v.x; q[j].y += v.y * v.y; q[j].z += v.z * v.z; q[j].w += v.w * v.w;
         }
@@ -222,13 +245,28 @@ gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const flo
   if (!m.active) return;
   GnCoef<NL> k;
   gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
-  for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
+  constexpr int U = PixUnroll<NL>::U;
+  for (int p0 = p_begin + m.sub; p0 < p_end; p0 += U * m.ppi) {
+    float4 vv[U][NL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pu = p0 + u * m.ppi;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const int l = m.t_lane + j * m.stride;
+        if (l < m.lanes && pu < p_end) vv[u][j] = ld_src(x, static_cast<long long>(n) * HW + pu, 4 * l);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+    const int p = p0 + u * m.ppi;
+    if (p >= p_end) break;
     const long long pix = static_cast<long long>(n) * HW + p;
 #pragma unroll
     for (int j = 0; j < NL; ++j) {
       const int l = m.t_lane + j * m.stride;
       if (l < m.lanes) {
-        const float4 v = ld_src(x, pix, 4 * l);
+        const float4 v = vv[u][j];
         float u0 = (v.x * k.rs[j].x + k.nm[j].x) * k.ga[j].x + k.be[j].x;
         float u1 = (v.y * k.rs[j].y + k.nm[j].y) * k.ga[j].y + k.be[j].y;
         float u2 = (v.z * k.rs[j].z + k.nm[j].z) * k.ga[j].z + k.be[j].z;
@@ -239,6 +277,7 @@ gn_apply_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const flo
         st_half4(y16 + pix * C + 4 * l, u0, u1, u2, u3);
         if (raw16 != nullptr) st_half4(raw16 + pix * C + 4 * l, v.x, v.y, v.z, v.w);
       }
+    }
     }
   }
 }
@@ -264,25 +303,43 @@ gn_bwd_reduce_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const f
     A[j] = make_float4(0, 0, 0, 0);
     Bq[j] = make_float4(0, 0, 0, 0);
   }
-  for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
-    const long long pix = static_cast<long long>(n) * HW + p;
+  constexpr int U = PixUnroll<NL>::U;
+  for (int p0 = p_begin + m.sub; p0 < p_end; p0 += U * m.ppi) {
+    float4 vv[U][NL], dd[U][NL];
 #pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      const int l = m.t_lane + j * m.stride;
-      if (l < m.lanes) {
-        const float4 v = ld_src(x, pix, 4 * l);
-        const float4 d = ld_dy<DY16>(dy, pix * C + 4 * l);
-        const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
-                             v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
-        const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
-        const float be[4] = {k.be[j].x, k.be[j].y, k.be[j].z, k.be[j].w};
-        float du[4] = {d.x, d.y, d.z, d.w};
-        if (silu) {
+    for (int u = 0; u < U; ++u) {
+      const int pu = p0 + u * m.ppi;
+      const long long pix = static_cast<long long>(n) * HW + pu;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) du[e] *= silu_grad(xh[e] * ga[e] + be[e]);
+      for (int j = 0; j < NL; ++j) {
+        const int l = m.t_lane + j * m.stride;
+        if (l < m.lanes && pu < p_end) {
+          vv[u][j] = ld_src(x, pix, 4 * l);
+          dd[u][j] = ld_dy<DY16>(dy, pix * C + 4 * l);
         }
-        A[j].x += du[0]; A[j].y += du[1]; A[j].z += du[2]; A[j].w += du[3];
-        Bq[j].x += du[0] * xh[0]; Bq[j].y += du[1] * xh[1]; Bq[j].z += du[2] * xh[2]; Bq[j].w += du[3] * xh[3];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u * m.ppi >= p_end) break;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const int l = m.t_lane + j * m.stride;
+        if (l < m.lanes) {
+          const float4 v = vv[u][j];
+          const float4 d = dd[u][j];
+          const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
+                               v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
+          const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
+          const float be[4] = {k.be[j].x, k.be[j].y, k.be[j].z, k.be[j].w};
+          float du[4] = {d.x, d.y, d.z, d.w};
+          if (silu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) du[e] *= silu_grad(xh[e] * ga[e] + be[e]);
+          }
+          A[j].x += du[0]; A[j].y += du[1]; A[j].z += du[2]; A[j].w += du[3];
+          Bq[j].x += du[0] * xh[0]; Bq[j].y += du[1] * xh[1]; Bq[j].z += du[2] * xh[2]; Bq[j].w += du[3] * xh[3];
+        }
       }
     }
   }
@@ -375,15 +432,34 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
       q2[j] = make_float4(b[0], b[1], b[2], b[3]);
     }
   }
-  for (int p = p_begin + m.sub; p < p_end; p += m.ppi) {
+  constexpr int U = PixUnroll<NL>::U;
+  for (int p0 = p_begin + m.sub; p0 < p_end; p0 += U * m.ppi) {
+    float4 vv[U][NL], dd[U][NL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pu = p0 + u * m.ppi;
+      const long long pixu = static_cast<long long>(n) * HW + pu;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const int l = m.t_lane + j * m.stride;
+        if (l < m.lanes && pu < p_end) {
+          vv[u][j] = ld_src(x, pixu, 4 * l);
+          dd[u][j] = ld_dy<DY16>(dy, pixu * C + 4 * l);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+    const int p = p0 + u * m.ppi;
+    if (p >= p_end) break;
     const long long pix = static_cast<long long>(n) * HW + p;
 #pragma unroll
     for (int j = 0; j < NL; ++j) {
       const int l = m.t_lane + j * m.stride;
       if (l < m.lanes) {
         const int c = 4 * l;
-        const float4 v = ld_src(x, pix, c);
-        const float4 d = ld_dy<DY16>(dy, pix * C + c);
+        const float4 v = vv[u][j];
+        const float4 d = dd[u][j];
         const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
                              v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
         const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
@@ -423,6 +499,7 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
         }
         *reinterpret_cast<float4*>(o) = outv;
       }
+    }
     }
   }
   if (dst.h16 != nullptr && dst.colsum != nullptr) {
