@@ -205,10 +205,15 @@ def run_ours(args):
         fused_attn = os.environ.get("MDM_UNFUSED_ATTENTION") is None
         flops = (FWD_GFLOP[cfg_name] - (ATTN_FWD_GFLOP if fused_attn else 0.0)) * 3 * B * 1e9
         ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear / attention)",
+        roof = {"bound": "tensor",
+                "kernel": "gemm_tc_persistent_kernel / gemm_tc_kernel (tcgen05 implicit-GEMM 3x3 conv + linear layers; "
+                          "the fused attention kernels are timed separately and excluded from these FLOPs)",
                 "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                "traffic": None, "traffic_note": "ncu --set full of the largest conv launch (profiles/r01_ncu_conv256_summary.txt): "
-                "351 MB DRAM vs 403 MB algorithmic (fp16 in, fp32 out) -> no re-reads", "peak_source": how, "launches_per_step": int(cnt.value // 2),
+                "traffic": 349.2e6,
+                "traffic_note": "bytes; ncu --set full of the largest conv launch (3x3 256->256 @ 64x64, batch 64; "
+                                "profiles/r01_ncu_conv256_v2_summary.txt): dram read 135.5 MB + write 213.7 MB vs 403.8 MB "
+                                "algorithmic (fp16 in, fp32 out) -> inputs read once, no re-reads",
+                "peak_source": how, "launches_per_step": int(cnt.value // 2),
                 "kernel_ms_per_step": round(gemm_ms, 3), "share_of_step": round(gemm_ms / (ms / args.steps), 3),
                 "algorithmic_flops_per_step": flops}
     if rank != 0:
