@@ -131,10 +131,17 @@ def run_ours(args):
     host = synthetic_host_batch(cfg_name, B, 1234 + rank)
     resident = {k: v.to(dev) for k, v in host.items()}
 
+    # gradient all-reduce: slices of the flat arena are reduced while backward is still running
+    overlap = parallel.GradientOverlap(vm) if world > 1 and os.environ.get("MDM_NO_OVERLAP") is None else None
+
     def step(sample):
         loss, *_ = pipe.get_loss(sample)
+        if overlap is not None:
+            overlap.arm()
         loss.mean().backward()
-        if world > 1:
+        if overlap is not None:
+            overlap.finish()
+        elif world > 1:
             parallel.allreduce_gradients(vm)
         return loss
 

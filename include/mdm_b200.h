@@ -159,6 +159,17 @@ typedef struct mdm_net_grad_io {
 /* Backward of the last mdm_net_forward(save_for_backward=1): accumulates parameter gradients. */
 int mdm_net_backward(mdm_net* net, const mdm_net_grad_io* gio, mdm_stream_t stream);
 
+/* Overlap of the data-parallel gradient all-reduce with backward (replaces DDP's bucket hooks,
+ * reference clis/train_parallel.py:147-154). While mdm_net_backward enqueues its kernels it calls
+ * fn(user, lo, hi) on the calling host thread each time another >= min_bytes of gradient memory became
+ * final: every bound gradient buffer that lies in the address range [lo, hi) has received its last
+ * write (as enqueued on `stream`), so a collective ordered after the current stream position may
+ * start on it. Ranges are reported from high addresses to low and never overlap; whatever was not reported
+ * (the first backward after create/structure change reports nothing) must be reduced by the caller
+ * afterwards. fn == NULL disables the notification. */
+typedef void (*mdm_grad_ready_fn)(void* user, void* lo, void* hi);
+int mdm_net_set_grad_ready(mdm_net* net, mdm_grad_ready_fn fn, void* user, uint64_t min_bytes);
+
 /* Device bytes currently reserved by the engine's pool / its high-water mark of live bytes. */
 uint64_t mdm_net_workspace_bytes(const mdm_net* net);
 uint64_t mdm_net_workspace_high_water(const mdm_net* net);

@@ -17,6 +17,8 @@
 
 #include <memory>
 
+#include <algorithm>
+
 #include "engine.cuh"
 #include "mdm_b200.h"
 
@@ -120,11 +122,27 @@ struct Net {
     pindex[name] = static_cast<int>(plist.size());
     plist.push_back(p);
   }
+  // ---- gradient-ready notification (mdm_net_set_grad_ready): which parameters each tape closure looks
+  // up is learned from earlier replays; while replaying, the addresses above the highest gradient any
+  // remaining closure may still touch are final and are reported so the caller can start reducing them.
+  mdm_grad_ready_fn ready_fn = nullptr;
+  void* ready_user = nullptr;
+  size_t ready_min_bytes = 0;
+  std::vector<std::vector<int>> learned;  // per closure (tape order): parameter indices seen during replay
+  int replay_idx = -1;                    // closure being replayed, -1 outside backward
+  std::vector<int> cur_lookup;
+  uintptr_t final_lo = UINTPTR_MAX;       // gradient addresses >= final_lo were reported final
+
   Param& P(const std::string& name) {
     auto it = pindex.find(name);
     if (it == pindex.end()) throw MdmFail("unknown parameter " + name);
     Param& p = plist[it->second];
     if (p.w == nullptr) throw MdmFail("parameter not bound: " + name);
+    if (replay_idx >= 0) {
+      cur_lookup.push_back(it->second);
+      if (p.g != nullptr && reinterpret_cast<uintptr_t>(p.g) >= final_lo)
+        throw MdmFail("gradient of " + name + " was reported ready before its last use in backward");
+    }
     return p;
   }
   void* persist(size_t bytes) {
@@ -1467,9 +1485,60 @@ struct Net {
       outs[l].d16 = eng.alloc<__half>(static_cast<long long>(B) * HW * 8);
       nchw_to_nhwc_f16(gio->dout[l], eng.d_scale, outs[l].d16, 8, B, cfg.out_channels, HW, st);
     }
-    for (auto it = eng.tape.rbegin(); it != eng.tape.rend(); ++it) (*it)();
+    replay_tape();
     eng.tape.clear();
     have_tape = false;
+  }
+
+  void replay_tape() {
+    const int n = static_cast<int>(eng.tape.size());
+    uintptr_t arena_lo = UINTPTR_MAX, arena_hi = 0;
+    for (const Param& p : plist) {
+      if (p.g == nullptr) continue;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(p.g);
+      arena_lo = std::min(arena_lo, a);
+      arena_hi = std::max(arena_hi, a + static_cast<uintptr_t>(p.numel) * sizeof(float));
+    }
+    const bool notify = ready_fn != nullptr && static_cast<int>(learned.size()) == n && n > 0 && arena_hi > arena_lo;
+    std::vector<uintptr_t> hi_prefix;  // highest gradient end address touched by closures 0..i
+    if (notify) {
+      hi_prefix.assign(n, arena_lo);
+      uintptr_t run = arena_lo;
+      for (int i = 0; i < n; ++i) {
+        for (int idx : learned[i]) {
+          const Param& p = plist[idx];
+          if (p.g != nullptr)
+            run = std::max(run, reinterpret_cast<uintptr_t>(p.g) + static_cast<uintptr_t>(p.numel) * sizeof(float));
+        }
+        hi_prefix[i] = run;
+      }
+    }
+    if (static_cast<int>(learned.size()) != n) learned.assign(n, {});
+    uintptr_t prev = arena_hi;
+    final_lo = UINTPTR_MAX;
+    struct Guard {
+      Net* n;
+      ~Guard() {
+        n->replay_idx = -1;
+        n->final_lo = UINTPTR_MAX;
+      }
+    } guard{this};
+    for (int i = n - 1; i >= 0; --i) {
+      replay_idx = i;
+      cur_lookup.clear();
+      eng.tape[i]();
+      std::vector<int>& seen = learned[i];
+      for (int idx : cur_lookup)
+        if (std::find(seen.begin(), seen.end(), idx) == seen.end()) seen.push_back(idx);
+      if (notify) {
+        const uintptr_t x = i > 0 ? hi_prefix[i - 1] : arena_lo;
+        if (x < prev && (prev - x >= ready_min_bytes || i == 0)) {
+          final_lo = x;
+          ready_fn(ready_user, reinterpret_cast<void*>(x), reinterpret_cast<void*>(prev));
+          prev = x;
+        }
+      }
+    }
   }
 };
 
@@ -1533,6 +1602,14 @@ int mdm_net_bind_param(mdm_net* net, const char* name, void* weight, void* grad)
     p.g = static_cast<float*>(grad);
     net->net.weights_dirty = true;
   })
+}
+
+int mdm_net_set_grad_ready(mdm_net* net, mdm_grad_ready_fn fn, void* user, uint64_t min_bytes) {
+  if (net == nullptr) return -1;
+  net->net.ready_fn = fn;
+  net->net.ready_user = user;
+  net->net.ready_min_bytes = static_cast<size_t>(min_bytes);
+  return 0;
 }
 
 int mdm_net_weights_changed(mdm_net* net) {

@@ -85,6 +85,10 @@ def lib():
     return _lib
 
 
+# void (*mdm_grad_ready_fn)(void* user, void* lo, void* hi)  (include/mdm_b200.h)
+GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
 def check(rc, what=""):
     if rc != 0:
         msg = lib().mdm_last_error().decode("utf-8", "replace")

@@ -159,6 +159,8 @@ class NativeNet:
         self.params = None
         self.sig = None
         self.grad_arena = None
+        self.active_arena = None
+        self._ready_cb = None
         self._keep = None
 
     def __del__(self):
@@ -308,9 +310,21 @@ class NativeNet:
             arena.zero_()
             views = self.grad_views
         st = torch.cuda.current_stream().cuda_stream
+        self.active_arena = arena  # what a gradient-ready callback (parallel.GradientOverlap) indexes into
         _lib.check(self.lib.mdm_net_backward(self.handle, C.byref(gio), C.c_void_p(st)), "mdm_net_backward")
         self._keep = None
         return [g if p.requires_grad else None for p, g in zip(self.params, views)]
+
+    def set_grad_ready(self, fn, min_bytes=0):
+        """Install (or with fn=None remove) the engine's gradient-ready notification: fn(lo_ptr, hi_ptr) is
+        called from inside mdm_net_backward whenever the gradient bytes at addresses [lo, hi) are final."""
+        if fn is None:
+            self._ready_cb = None
+            _lib.check(self.lib.mdm_net_set_grad_ready(self.handle, None, None, C.c_uint64(0)), "set_grad_ready")
+            return
+        cb = _lib.GRAD_READY_FN(lambda user, lo, hi: fn(int(lo or 0), int(hi or 0)))
+        self._ready_cb = cb  # keep the trampoline alive as long as the engine may call it
+        _lib.check(self.lib.mdm_net_set_grad_ready(self.handle, cb, None, C.c_uint64(int(min_bytes))), "set_grad_ready")
 
     def workspace_bytes(self):
         return int(self.lib.mdm_net_workspace_bytes(self.handle)), int(self.lib.mdm_net_workspace_high_water(self.handle))

@@ -41,6 +41,93 @@ def allreduce_gradients(module, group=None, average=True):
     return allreduce_tensors(bucket, group=group, average=average)
 
 
+class GradientOverlap:
+    """Gradient all-reduce overlapped with backward (what DDP's bucket hooks do for the reference,
+    clis/train_parallel.py:147-154). The engine reports, while it is still enqueuing backward kernels,
+    every further `bucket_mb` of the flat gradient arena that has received its last write
+    (mdm_net_set_grad_ready, include/mdm_b200.h); each report starts an asynchronous all-reduce of that
+    slice, which NCCL orders after the kernels enqueued so far and runs on its own stream next to the
+    rest of backward.
+
+        overlap = GradientOverlap(pipeline.get_model().vision_model)   # once
+        overlap.arm(); loss.backward(); overlap.finish()               # every synchronising step
+    (a backward without arm() is left alone, which is the `no_sync` accumulation case)
+
+    finish() reduces whatever was not reported (everything, on the first step, while the engine learns
+    which closure touches which parameter) and makes the current stream wait for all collectives."""
+
+    def __init__(self, module, group=None, average=True, bucket_mb=64):
+        self.module, self.group, self.average = module, group, average
+        self.works, self.low = [], None
+        self.armed = False
+        self.segments = []  # (lo, hi) element ranges reduced during the last step, in issue order
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        native = module.native() if hasattr(module, "native") else getattr(module, "_native", None)
+        self.native = native
+        if self.enabled and native is not None:
+            native.set_grad_ready(self._on_ready, int(bucket_mb) << 20)
+
+    def close(self):
+        if self.native is not None:
+            self.native.set_grad_ready(None)
+
+    def _reduce(self, t, async_op):
+        world = dist.get_world_size(self.group)
+        if self.average and t.is_cuda:
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        if self.average:
+            if w is not None:
+                w.wait()
+            t.div_(world)
+        return w
+
+    def arm(self):
+        """The next backward's gradients are to be reduced (call right before loss.backward())."""
+        self.armed = True
+        self.works, self.low, self.segments = [], None, []
+
+    def _on_ready(self, lo_ptr, hi_ptr, arena=None):
+        if not self.armed:
+            return
+        if arena is None:
+            arena = self.native.active_arena
+            if arena is not self.native.grad_arena:
+                return  # gradients are being accumulated into existing .grad tensors: reduce at the end
+        base, n = arena.data_ptr(), arena.numel()
+        lo = min(max((lo_ptr - base) // arena.element_size(), 0), n)
+        hi = min(max((hi_ptr - base) // arena.element_size(), 0), n)
+        if self.low is None:
+            self.segments = []
+        if hi > lo:
+            self.works.append(self._reduce(arena[lo:hi], async_op=True))
+            self.segments.append((lo, hi))
+        self.low = lo if self.low is None else min(self.low, lo)
+
+    def finish(self, arena=None):
+        """Reduce the part of the arena no report covered, then join the collectives."""
+        if not self.enabled:
+            return 0
+        self.armed = False
+        if arena is None:
+            arena = flat_grads(self.module)
+        if arena is None:  # gradients are not in the arena (accumulation): plain path
+            self.works, self.low = [], None
+            return allreduce_gradients(self.module, group=self.group, average=self.average)
+        rest = arena.numel() if self.low is None else self.low
+        if self.low is None:
+            self.segments = []
+        if rest > 0:
+            self.works.append(self._reduce(arena[:rest], async_op=True))
+            self.segments.append((0, rest))
+        for w in self.works:
+            if w is not None:
+                w.wait()
+        n = len(self.works)
+        self.works, self.low = [], None
+        return n
+
+
 def allreduce_tensors(tensors, group=None, average=True):
     """Fallback for gradients that are not in the arena (e.g. accumulation mode): flatten once."""
     if not tensors:

@@ -127,3 +127,53 @@ def test_shipped_config_forward_vs_oracle_full_width(name):
     outs = list(out) if nested else [out]
     for o, r in zip(outs, refs):
         assert nc.rel(o.cpu(), r) <= 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["unet", "nested"])
+def test_grad_ready_ranges_are_final(kind):
+    """mdm_net_set_grad_ready (include/mdm_b200.h): every address range reported during backward must
+    already hold its final values in stream order (this is what lets the data-parallel all-reduce start
+    before backward has finished, parallel.GradientOverlap). A snapshot enqueued inside the callback is
+    compared bit-for-bit with the arena after backward."""
+    import tiny_configs as tc
+    nlev = 1 if kind == "unet" else 2
+    res = 16 if kind == "unet" else 32
+    model, _, _ = nc.build(kind)
+    model = model.cuda()
+    x, t, lm, mask = tc.seeded_inputs(3, 2, res, 6, nlevels=nlev)
+    xs = [x.cuda()] if nlev == 1 else [xi.cuda() for xi in x]
+    native = model.native()
+    snaps = []
+
+    def on_ready(lo, hi):
+        arena = native.active_arena
+        a = (lo - arena.data_ptr()) // 4
+        b = (hi - arena.data_ptr()) // 4
+        assert 0 <= a < b <= arena.numel()
+        snaps.append((a, b, arena[a:b].clone()))  # enqueued at this point of the backward stream
+
+    def step():
+        out = model(xs if nlev > 1 else xs[0], t.cuda(), lm.cuda(), mask.cuda(), {})
+        outs = [out] if nlev == 1 else list(out)
+        sum((o * o).sum() for o in outs).backward()
+        torch.cuda.synchronize()
+
+    native_bytes_hint = 0  # report every newly final byte
+    step()                       # the engine learns which closure touches which parameter
+    model.zero_grad(set_to_none=True)
+    native.set_grad_ready(on_ready, native_bytes_hint)
+    step()
+    native.set_grad_ready(None)
+    assert len(snaps) >= 3, "no gradient range was reported during the second backward"
+    arena = native.grad_arena
+    covered = 0
+    prev_lo = arena.numel()
+    for a, b, snap in snaps:
+        assert b == prev_lo, "ranges must tile the arena from the top down without gaps or overlap"
+        prev_lo = a
+        covered += b - a
+        assert torch.equal(snap, arena[a:b]), f"gradient range [{a},{b}) changed after it was reported final"
+    assert prev_lo == 0 and covered == arena.numel()
+    # and the step still produced non-trivial gradients
+    assert float(arena.abs().max()) > 0

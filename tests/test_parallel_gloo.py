@@ -46,6 +46,39 @@ def _worker(rank, world, port, q):
             p.grad = torch.full_like(p, float(rank))
         parallel.allreduce_gradients(lin2)
         assert torch.allclose(lin2.bias.grad, torch.full((2,), 0.5))
+        # overlapped reduction: the engine reports final address ranges from the top of the arena downwards
+        # (simulated here); finish() must cover the rest exactly once
+        class FakeNative(Fake):
+            def set_grad_ready(self, fn, min_bytes=0):
+                self.fn = fn
+
+        lin3 = torch.nn.Linear(5, 4)
+        n3 = sum(p.numel() for p in lin3.parameters())
+        arena3 = torch.zeros(n3)
+        off = 0
+        for p in lin3.parameters():
+            p.grad = arena3[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        nat3 = FakeNative()
+        nat3.grad_arena, nat3.active_arena, nat3.params = arena3, arena3, list(lin3.parameters())
+        lin3._native = nat3
+        ov = parallel.GradientOverlap(lin3, bucket_mb=1)
+        assert ov.enabled and nat3.fn is not None
+        base = arena3.data_ptr()
+        for step_i in range(2):
+            arena3.copy_(torch.arange(n3, dtype=torch.float32) * (rank + 1))
+            if step_i == 1:
+                ov.arm()
+                nat3.fn(base + 4 * 16, base + 4 * n3)   # [16, n3) final
+                nat3.fn(base + 4 * 6, base + 4 * 16)    # [6, 16) final
+            # step 0: no reports at all (the engine's learning step)
+            ncalls = ov.finish()
+            assert ncalls == (3 if step_i == 1 else 1), ncalls
+            assert torch.allclose(arena3, torch.arange(n3, dtype=torch.float32) * 1.5), arena3
+        assert ov.segments == [(16, n3), (6, 16), (0, 6)], ov.segments
+        # an un-armed backward (accumulation step) must not start any collective
+        nat3.fn(base, base + 4 * n3)
+        assert ov.works == [] and ov.low is None
         q.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         q.put((rank, repr(e)))
