@@ -131,8 +131,12 @@ def run_ours(args):
     host = synthetic_host_batch(cfg_name, B, 1234 + rank)
     resident = {k: v.to(dev) for k, v in host.items()}
 
-    # gradient all-reduce: slices of the flat arena are reduced while backward is still running
-    overlap = parallel.GradientOverlap(vm) if world > 1 and os.environ.get("MDM_NO_OVERLAP") is None else None
+    # Gradient all-reduce: one NCCL call over the flat arena after backward. MDM_OVERLAP=1 instead reduces
+    # slices of the arena while backward is still running (parallel.GradientOverlap); measured at N=2 that is
+    # not faster yet (782 vs 792 sample-steps/s: NCCL's copy CTAs and the one-CTA-per-SM persistent GEMM
+    # compete for SMs), so it is opt-in.
+    overlap = (parallel.GradientOverlap(vm, bucket_mb=int(os.environ.get("MDM_BUCKET_MB", "64")))
+               if world > 1 and os.environ.get("MDM_OVERLAP") is not None else None)
 
     def step(sample):
         loss, *_ = pipe.get_loss(sample)

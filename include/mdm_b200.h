@@ -169,6 +169,11 @@ int mdm_net_backward(mdm_net* net, const mdm_net_grad_io* gio, mdm_stream_t stre
  * afterwards. fn == NULL disables the notification. */
 typedef void (*mdm_grad_ready_fn)(void* user, void* lo, void* hi);
 int mdm_net_set_grad_ready(mdm_net* net, mdm_grad_ready_fn fn, void* user, uint64_t min_bytes);
+/* After at least one mdm_net_backward: rank[i] = how late the gradient of parameter i (mdm_net_param_info
+ * index) becomes final, as the index of the last backward closure that uses it (0 = final only at the very
+ * end, larger = earlier, INT32_MAX = never written). Gradient buffers laid out in ascending rank order
+ * make the notification above cover the arena from the top down. Returns -1 before the first backward. */
+int mdm_net_grad_order(const mdm_net* net, int32_t* rank, int32_t n);
 
 /* Device bytes currently reserved by the engine's pool / its high-water mark of live bytes. */
 uint64_t mdm_net_workspace_bytes(const mdm_net* net);

@@ -1513,6 +1513,17 @@ struct Net {
         hi_prefix[i] = run;
       }
     }
+    if (notify && getenv("MDM_DEBUG_GRAD_READY") != nullptr) {
+      // which closure pins how much of the arena: the highest gradient each of the earliest closures touches
+      for (int i = 0; i < n && i < 12; ++i) {
+        const Param* top = nullptr;
+        for (int idx : learned[i])
+          if (plist[idx].g != nullptr && (top == nullptr || plist[idx].g > top->g)) top = &plist[idx];
+        fprintf(stderr, "[grad_ready] closure %d/%d: %zu params, highest %s at +%.1f MB of %.1f MB\n", i, n,
+                learned[i].size(), top ? top->name.c_str() : "-",
+                top ? (reinterpret_cast<uintptr_t>(top->g) - arena_lo) / 1048576.0 : 0.0, (arena_hi - arena_lo) / 1048576.0);
+      }
+    }
     if (static_cast<int>(learned.size()) != n) learned.assign(n, {});
     uintptr_t prev = arena_hi;
     final_lo = UINTPTR_MAX;
@@ -1602,6 +1613,16 @@ int mdm_net_bind_param(mdm_net* net, const char* name, void* weight, void* grad)
     p.g = static_cast<float*>(grad);
     net->net.weights_dirty = true;
   })
+}
+
+int mdm_net_grad_order(const mdm_net* net, int32_t* rank, int32_t n) {
+  if (net == nullptr || rank == nullptr) return -1;
+  const mdm::Net& N = net->net;
+  if (N.learned.empty() || n != static_cast<int32_t>(N.plist.size())) return -1;
+  for (int32_t i = 0; i < n; ++i) rank[i] = INT32_MAX;
+  for (size_t c = 0; c < N.learned.size(); ++c)
+    for (int idx : N.learned[c]) rank[idx] = std::min<int32_t>(rank[idx], static_cast<int32_t>(c));
+  return 0;
 }
 
 int mdm_net_set_grad_ready(mdm_net* net, mdm_grad_ready_fn fn, void* user, uint64_t min_bytes) {

@@ -160,6 +160,7 @@ class NativeNet:
         self.sig = None
         self.grad_arena = None
         self.active_arena = None
+        self.order = None
         self._ready_cb = None
         self._keep = None
 
@@ -205,11 +206,17 @@ class NativeNet:
         total = sum(p.numel() for k, p in plist if not k.endswith("t_emb"))
         self.grad_arena = torch.zeros(total, device=dev, dtype=torch.float32)
         off = 0
-        self.params, self.grad_views = [], []
+        self.params, self.grad_views, self.param_names = [], [], []
+        # Arena layout: registration order at first; optimize_arena_layout() re-sorts it by how late each
+        # gradient becomes final so that mdm_net_set_grad_ready can report it from the top down.
+        if self.order is not None:
+            by_name = dict(plist)
+            plist = [(k, by_name[k]) for k in self.order]
         for k, p in plist:
             if k.endswith("t_emb"):
                 _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()), None), "bind")
                 continue
+            self.param_names.append(k)
             g = self.grad_arena[off:off + p.numel()].view_as(p)
             off += p.numel()
             _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
@@ -302,7 +309,7 @@ class NativeNet:
                 g = arena[off:off + p.numel()].view_as(p)
                 off += p.numel()
                 views.append(g)
-            for k, p, g in zip([n for n in self.names if not n.endswith("t_emb")], self.params, views):
+            for k, p, g in zip(self.param_names, self.params, views):
                 _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
                                                        C.c_void_p(g.data_ptr())), "bind")
             self.sig = None  # rebinding to the persistent arena happens at the next forward
@@ -314,6 +321,22 @@ class NativeNet:
         _lib.check(self.lib.mdm_net_backward(self.handle, C.byref(gio), C.c_void_p(st)), "mdm_net_backward")
         self._keep = None
         return [g if p.requires_grad else None for p, g in zip(self.params, views)]
+
+    def optimize_arena_layout(self):
+        """Re-sort the gradient arena by the order gradients become final in backward (learned by the
+        engine during a previous backward, mdm_net_grad_order), latest at the lowest address. Returns
+        False when nothing has been learned yet. Takes effect at the next forward; gradients already
+        handed out keep their (old) storage."""
+        n = len(self.names)
+        rank = (C.c_int32 * n)()
+        if self.lib.mdm_net_grad_order(self.handle, rank, C.c_int32(n)) != 0:
+            return False
+        idx = sorted(range(n), key=lambda i: (rank[i], i))
+        order = [self.names[i] for i in idx]
+        if order != self.order:
+            self.order = order
+            self.sig = None  # rebind at the next forward
+        return True
 
     def set_grad_ready(self, fn, min_bytes=0):
         """Install (or with fn=None remove) the engine's gradient-ready notification: fn(lo_ptr, hi_ptr) is

@@ -60,6 +60,7 @@ class GradientOverlap:
         self.module, self.group, self.average = module, group, average
         self.works, self.low = [], None
         self.armed = False
+        self.laid_out = False
         self.segments = []  # (lo, hi) element ranges reduced during the last step, in issue order
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         native = module.native() if hasattr(module, "native") else getattr(module, "_native", None)
@@ -125,6 +126,9 @@ class GradientOverlap:
                 w.wait()
         n = len(self.works)
         self.works, self.low = [], None
+        if not self.laid_out and self.native is not None and hasattr(self.native, "optimize_arena_layout"):
+            # after the first backward the engine knows when each gradient becomes final
+            self.laid_out = bool(self.native.optimize_arena_layout())
         return n
 
 

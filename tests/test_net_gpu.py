@@ -162,6 +162,7 @@ def test_grad_ready_ranges_are_final(kind):
     native_bytes_hint = 0  # report every newly final byte
     step()                       # the engine learns which closure touches which parameter
     model.zero_grad(set_to_none=True)
+    assert native.optimize_arena_layout()   # arena re-sorted by gradient finalisation order
     native.set_grad_ready(on_ready, native_bytes_hint)
     step()
     native.set_grad_ready(None)
