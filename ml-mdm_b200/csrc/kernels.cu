@@ -532,25 +532,32 @@ cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, lon
   if (!m.active) return;
   float4 s = make_float4(0, 0, 0, 0);
   const int c = c0 + 4 * m.t_lane;
-  for (long long r = r_begin + m.sub; r < r_end; r += 2 * m.ppi) {
-    float4 v[2];
+  constexpr int U = 4;  // rows per trip: all loads issued before the first use
+  for (long long r = r_begin + m.sub; r < r_end; r += U * m.ppi) {
+    float4 v[U];
+    uint2 raw[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long rr = r + static_cast<long long>(u) * m.ppi;
       v[u] = make_float4(0, 0, 0, 0);
+      raw[u] = make_uint2(0, 0);
       if (rr < r_end) {
-        if (IN_F16) {
-          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(in_) + rr * C + c));
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-          v[u] = make_float4(a.x, a.y, b.x, b.y);
-        } else {
-          v[u] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in_) + rr * C + c));
-          if (out16 != nullptr) st_half4(out16 + rr * C + c, v[u].x, v[u].y, v[u].z, v[u].w);
-        }
+        if (IN_F16) raw[u] = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(in_) + rr * C + c));
+        else v[u] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in_) + rr * C + c));
       }
     }
-    s.x += v[0].x + v[1].x; s.y += v[0].y + v[1].y; s.z += v[0].z + v[1].z; s.w += v[0].w + v[1].w;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * m.ppi;
+      if (IN_F16) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
+        v[u] = make_float4(a.x, a.y, b.x, b.y);
+      } else if (out16 != nullptr && rr < r_end) {
+        st_half4(out16 + rr * C + c, v[u].x, v[u].y, v[u].z, v[u].w);
+      }
+      s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+    }
   }
   if (colsum == nullptr) return;
   const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
