@@ -1,4 +1,6 @@
 // Streaming (HBM-bound) kernels of the denoising path. See kernels.cuh for the contracts.
+#include <stdexcept>
+
 #include "kernels.cuh"
 
 #include <math.h>
@@ -1067,17 +1069,22 @@ __global__ void pack_conv_in_w_kernel(const float* __restrict__ w, __half* __res
   }
   p[i] = __float2half_rn(v);
 }
-__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci,
-                                         int taps, int ci_ld, const float* __restrict__ inv_scale) {
-  const long long total = static_cast<long long>(Co) * Ci;
-  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+// packed [Co][taps][ci_ld] -> g [Co][Ci][taps] (+=). One CTA per (co, 256 input channels): coalesced reads per
+// tap, transpose through shared memory (row stride `taps` = 9 words is odd: conflict-free), contiguous writes.
+__global__ void __launch_bounds__(256)
+unpack_conv_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps,
+                         int ci_ld, const float* __restrict__ inv_scale) {
+  __shared__ float sm[9 * 256];
+  const int co = blockIdx.x;
+  const int ci0 = blockIdx.y * 256;
+  const int n = min(256, Ci - ci0);
   const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
-  for (; i < total; i += gs) {
-    const int ci = static_cast<int>(i % Ci);
-    const long long co = i / Ci;
-    for (int t = 0; t < taps; ++t) g[i * taps + t] += inv * packed[(co * taps + t) * ci_ld + ci];
-  }
+  if (static_cast<int>(threadIdx.x) < n)
+    for (int t = 0; t < taps; ++t)
+      sm[threadIdx.x * taps + t] = packed[(static_cast<long long>(co) * taps + t) * ci_ld + ci0 + threadIdx.x];
+  __syncthreads();
+  float* dst = g + (static_cast<long long>(co) * Ci + ci0) * taps;
+  for (int idx = threadIdx.x; idx < n * taps; idx += 256) dst[idx] += inv * sm[idx];
 }
 __global__ void unpack_conv_in_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co,
                                             int Ci, const float* __restrict__ inv_scale) {
@@ -1330,8 +1337,9 @@ void pack_conv_in_w(const float* w_oihw, __half* packed, int Co, int Ci, cudaStr
 }
 void unpack_conv_wgrad(const float* packed, float* g_oihw, int Co, int Ci, int taps, int ci_ld,
                        const float* inv_scale, cudaStream_t st) {
-  unpack_conv_wgrad_kernel<<<grid_for(static_cast<long long>(Co) * Ci), 256, 0, st>>>(packed, g_oihw, Co, Ci, taps,
-                                                                                     ci_ld, inv_scale);
+  if (taps > 9) throw std::runtime_error("unpack_conv_wgrad: at most 9 taps");
+  unpack_conv_wgrad_kernel<<<dim3(Co, static_cast<unsigned>(cdiv(Ci, 256))), 256, 0, st>>>(packed, g_oihw, Co, Ci, taps,
+                                                                                          ci_ld, inv_scale);
   MDM_LAUNCHED();
 }
 void unpack_conv_in_wgrad(const float* packed, float* g_oihw, int Co, int Ci, const float* inv_scale,
