@@ -183,6 +183,46 @@ uint64_t mdm_net_workspace_high_water(const mdm_net* net);
 int64_t mdm_net_debug_fetch(mdm_net* net, const char* name, float* dst, int64_t max_elems, mdm_stream_t stream);
 
 
+/* ---------------------------------------------------------------- post-backward sweep
+ * Replaces, in one pass over the flat gradient arena, the reference's
+ *   nn.utils.clip_grad_norm_(model.parameters(), clip)      ml_mdm/trainer.py:78-80
+ *   optimizer.step()  (torch.optim.Adam / AdamW)            ml_mdm/trainer.py:81, clis/train_parallel.py:122-134
+ *   ema_model.update(vision_model)                          ml_mdm/trainer.py:82-85, models/model_ema.py:25-34
+ *   optimizer.zero_grad()                                   ml_mdm/trainer.py:92-93
+ * All pointers are device fp32. */
+
+/* One contiguous run of parameters (a tensor or a slice of one). ema may be NULL. */
+typedef struct mdm_opt_chunk {
+  float* p;   /* parameter values, updated in place */
+  float* g;   /* gradient (read; overwritten with 0 when zero_grad, else with the scaled/clipped value) */
+  float* m;   /* Adam exp_avg */
+  float* v;   /* Adam exp_avg_sq */
+  float* ema; /* EMA copy of p, or NULL */
+  int64_t n;  /* elements */
+} mdm_opt_chunk;
+
+typedef struct mdm_adam_cfg {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t adamw;       /* 0: Adam (L2 added to the gradient), 1: AdamW (decoupled decay) */
+  int32_t step;        /* 1-based step count of this update (bias corrections 1 - beta^step) */
+  float grad_scale;    /* gradients are multiplied by this first (1/world, 1/accumulation, ...) */
+  float max_norm;      /* clip_grad_norm_ threshold on the scaled gradients; <= 0 disables clipping */
+  float ema_decay;     /* effective decay of this EMA update: (counter >= warmup) * decay (model_ema.py:26) */
+  int32_t zero_grad;   /* 1: leave the gradients zeroed (the next backward needs no memset) */
+} mdm_adam_cfg;
+
+#define MDM_GRAD_NORM_SCRATCH 1184 /* doubles of scratch mdm_grad_norm needs */
+/* out_norm[0] = grad_scale * sqrt(sum grads[i]^2) over the n elements (gaps of the arena must be zero), left on
+ * the device; deterministic (fixed reduction tree, fp64 partial sums). */
+int mdm_grad_norm(const float* grads, int64_t n, float grad_scale, double* scratch, int32_t scratch_elems,
+                  float* out_norm, mdm_stream_t stream);
+/* chunks_dev: device array of nchunks descriptors (one CTA each; keep n <= ~64K per chunk). norm_dev is the
+ * value written by mdm_grad_norm (may be NULL when max_norm <= 0). Element formulas follow
+ * torch/optim/adam.py::_single_tensor_adam, torch/nn/utils/clip_grad.py and ModelEma.update op for op. */
+int mdm_adam_ema_sweep(const mdm_opt_chunk* chunks_dev, int32_t nchunks, const mdm_adam_cfg* cfg,
+                       const float* norm_dev, mdm_stream_t stream);
+
+
 /* ---------------------------------------------------------------- diffusion algebra (NCHW fp32) */
 /* gammas: device fp32 table of num_diffusion_steps+1 entries (Sampler.gammas, samplers.py:201-231),
  * for nested pipelines the per-level shifted table (samplers.py:255-264,613-623).

@@ -134,6 +134,13 @@ class _DenoiseFn(torch.autograd.Function):
         return (None,) * 7 + (None,) * ctx.nlev + tuple(grads)
 
 
+ARENA_ALIGN = 64  # elements: every gradient view starts on a 256-byte boundary (vector loads in the optimiser sweep)
+
+
+def _pad(n):
+    return (n + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+
+
 class NativeNet:
     def __init__(self, module):
         self.module = module
@@ -161,6 +168,8 @@ class NativeNet:
         self.grad_arena = None
         self.active_arena = None
         self.order = None
+        self.arena_zeroed = False
+        self.offsets = None
         self._ready_cb = None
         self._keep = None
 
@@ -203,10 +212,11 @@ class NativeNet:
         if sig == self.sig:
             return
         dev = plist[0][1].device
-        total = sum(p.numel() for k, p in plist if not k.endswith("t_emb"))
+        total = sum(_pad(p.numel()) for k, p in plist if not k.endswith("t_emb"))
         self.grad_arena = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.arena_zeroed = True
         off = 0
-        self.params, self.grad_views, self.param_names = [], [], []
+        self.params, self.grad_views, self.param_names, self.offsets = [], [], [], []
         # Arena layout: registration order at first; optimize_arena_layout() re-sorts it by how late each
         # gradient becomes final so that mdm_net_set_grad_ready can report it from the top down.
         if self.order is not None:
@@ -217,8 +227,9 @@ class NativeNet:
                 _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()), None), "bind")
                 continue
             self.param_names.append(k)
+            self.offsets.append(off)
             g = self.grad_arena[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += _pad(p.numel())
             _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
                                                    C.c_void_p(g.data_ptr())), "bind")
             self.params.append(p)
@@ -303,18 +314,15 @@ class NativeNet:
         aliased = any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params)
         if aliased:
             arena = torch.zeros_like(self.grad_arena)
-            off = 0
-            views = []
-            for p in self.params:
-                g = arena[off:off + p.numel()].view_as(p)
-                off += p.numel()
-                views.append(g)
+            views = [arena[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
             for k, p, g in zip(self.param_names, self.params, views):
                 _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
                                                        C.c_void_p(g.data_ptr())), "bind")
             self.sig = None  # rebinding to the persistent arena happens at the next forward
         else:
-            arena.zero_()
+            if not self.arena_zeroed:  # the fused optimiser sweep (optim.FusedAdam) leaves it zeroed
+                arena.zero_()
+            self.arena_zeroed = False
             views = self.grad_views
         st = torch.cuda.current_stream().cuda_stream
         self.active_arena = arena  # what a gradient-ready callback (parallel.GradientOverlap) indexes into
