@@ -202,12 +202,14 @@ typedef struct mdm_opt_chunk {
 } mdm_opt_chunk;
 
 typedef struct mdm_adam_cfg {
-  float lr, beta1, beta2, eps, weight_decay;
-  int32_t adamw;       /* 0: Adam (L2 added to the gradient), 1: AdamW (decoupled decay) */
-  int32_t step;        /* 1-based step count of this update (bias corrections 1 - beta^step) */
+  /* hyper-parameters as the doubles torch holds them: the float constants the kernels use (1 - beta, lr / (1 -
+   * beta1^step), sqrt(1 - beta2^step), 1 - lr * wd, 1 - ema_decay) are derived in double first, like torch does */
+  double lr, beta1, beta2, eps, weight_decay;
+  double ema_decay;    /* effective decay of this EMA update: (counter >= warmup) * decay (model_ema.py:26) */
   float grad_scale;    /* gradients are multiplied by this first (1/world, 1/accumulation, ...) */
   float max_norm;      /* clip_grad_norm_ threshold on the scaled gradients; <= 0 disables clipping */
-  float ema_decay;     /* effective decay of this EMA update: (counter >= warmup) * decay (model_ema.py:26) */
+  int32_t adamw;       /* 0: Adam (L2 added to the gradient), 1: AdamW (decoupled decay) */
+  int32_t step;        /* 1-based step count of this update (bias corrections 1 - beta^step) */
   int32_t zero_grad;   /* 1: leave the gradients zeroed (the next backward needs no memset) */
 } mdm_adam_cfg;
 

@@ -13,6 +13,9 @@
 #include "engine.cuh"
 #include "mdm_b200.h"
 
+static_assert(sizeof(mdm_opt_chunk) == 48, "mdm_opt_chunk layout is part of the ABI (optim.py mirrors it)");
+static_assert(sizeof(mdm_adam_cfg) == 72, "mdm_adam_cfg layout is part of the ABI (optim.py mirrors it)");
+
 namespace mdm {
 
 namespace {
@@ -65,28 +68,27 @@ __global__ void __launch_bounds__(SQ_THREADS) sqnorm_final_kernel(const double* 
 
 struct SweepScalars {
   float grad_scale, max_norm;  // max_norm <= 0: no clipping
-  float lr, beta1, beta2, eps, weight_decay;
-  float bc1, bc2_sqrt;         // 1 - beta1^t, sqrt(1 - beta2^t), computed in double on the host like torch
-  float ema_decay;             // effective decay of this update (0 during EMA warm-up)
-  int adamw, zero_grad, has_ema;
+  float one_m_beta1, beta2, one_m_beta2, eps;
+  float weight_decay, decay_mul;   // Adam L2 coefficient; AdamW factor 1 - lr * wd
+  float step_size, bc2_sqrt;       // lr / (1 - beta1^t), sqrt(1 - beta2^t): computed in double on the host like torch
+  float ema_decay, one_m_ema;      // effective decay of this update (0 during EMA warm-up) and 1 - decay
+  int adamw, zero_grad;
 };
 
-// One element, op for op as torch applies it (torch/optim/adam.py::_single_tensor_adam, no amsgrad / maximize),
-// with the roundings torch's separate kernels have: plain mul/add where torch runs separate ops, fma only where
-// torch's kernel fuses (addcmul_, addcdiv_, lerp_).
+// One element, op for op as torch applies it (torch/optim/adam.py::_single_tensor_adam, no amsgrad / maximize):
+// every Python scalar enters as the float torch would cast it to.
 __device__ __forceinline__ void adam_elem(float& p, float& g, float& m, float& v, float* ema, float clip,
                                           const SweepScalars& s) {
   float gr = __fmul_rn(g, clip);
   if (s.weight_decay != 0.f) {
-    if (s.adamw) p = __fmul_rn(p, 1.f - s.lr * s.weight_decay);   // param.mul_(1 - lr * wd)
+    if (s.adamw) p = __fmul_rn(p, s.decay_mul);                   // param.mul_(1 - lr * wd)
     else gr = fmaf(p, s.weight_decay, gr);                       // grad.add(param, alpha = wd)
   }
-  m = fmaf(1.f - s.beta1, __fsub_rn(gr, m), m);                   // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(__fmul_rn(1.f - s.beta2, gr), gr, __fmul_rn(v, s.beta2));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
+  m = fmaf(s.one_m_beta1, __fsub_rn(gr, m), m);                   // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(__fmul_rn(s.one_m_beta2, gr), gr, __fmul_rn(v, s.beta2));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
   const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
-  const float step_size = s.lr / s.bc1;
-  p = fmaf(-step_size, __fdiv_rn(m, denom), p);                   // param.addcdiv_(exp_avg, denom, value=-step)
-  if (ema != nullptr) *ema = fmaf(p, 1.f - s.ema_decay, __fmul_rn(*ema, s.ema_decay));  // mul_(d).add_(p, alpha=1-d)
+  p = fmaf(-s.step_size, __fdiv_rn(m, denom), p);                 // param.addcdiv_(exp_avg, denom, value=-step)
+  if (ema != nullptr) *ema = fmaf(p, s.one_m_ema, __fmul_rn(*ema, s.ema_decay));  // mul_(d).add_(p, alpha=1-d)
   g = s.zero_grad ? 0.f : gr;
 }
 
@@ -162,19 +164,22 @@ int mdm_adam_ema_sweep(const mdm_opt_chunk* chunks_dev, int32_t nchunks, const m
     MDM_CHECK(cfg->max_norm <= 0.f || norm_dev != nullptr, "clipping needs the device norm (mdm_grad_norm)");
     if (nchunks <= 0) return 0;
     mdm::SweepScalars s;
+    const double bc1 = 1.0 - pow(cfg->beta1, static_cast<double>(cfg->step));
+    const double bc2 = 1.0 - pow(cfg->beta2, static_cast<double>(cfg->step));
     s.grad_scale = cfg->grad_scale;
     s.max_norm = cfg->max_norm;
-    s.lr = cfg->lr;
-    s.beta1 = cfg->beta1;
-    s.beta2 = cfg->beta2;
-    s.eps = cfg->eps;
-    s.weight_decay = cfg->weight_decay;
-    s.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(cfg->beta1), static_cast<double>(cfg->step)));
-    s.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(cfg->beta2), static_cast<double>(cfg->step))));
-    s.ema_decay = cfg->ema_decay;
+    s.one_m_beta1 = static_cast<float>(1.0 - cfg->beta1);
+    s.beta2 = static_cast<float>(cfg->beta2);
+    s.one_m_beta2 = static_cast<float>(1.0 - cfg->beta2);
+    s.eps = static_cast<float>(cfg->eps);
+    s.weight_decay = static_cast<float>(cfg->weight_decay);
+    s.decay_mul = static_cast<float>(1.0 - cfg->lr * cfg->weight_decay);
+    s.step_size = static_cast<float>(cfg->lr / bc1);
+    s.bc2_sqrt = static_cast<float>(sqrt(bc2));
+    s.ema_decay = static_cast<float>(cfg->ema_decay);
+    s.one_m_ema = static_cast<float>(1.0 - cfg->ema_decay);
     s.adamw = cfg->adamw;
     s.zero_grad = cfg->zero_grad;
-    s.has_ema = 1;
     mdm::adam_ema_sweep_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(chunks_dev, norm_dev, s);
     ++mdm::g_launch_count;
     MDM_CUDA(cudaGetLastError());

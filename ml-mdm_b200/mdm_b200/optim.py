@@ -22,9 +22,9 @@ class OptChunk(C.Structure):  # mirrors mdm_opt_chunk (include/mdm_b200.h)
 
 
 class AdamCfg(C.Structure):  # mirrors mdm_adam_cfg
-    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("weight_decay", C.c_float), ("adamw", C.c_int32), ("step", C.c_int32), ("grad_scale", C.c_float),
-                ("max_norm", C.c_float), ("ema_decay", C.c_float), ("zero_grad", C.c_int32)]
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("ema_decay", C.c_double), ("grad_scale", C.c_float),
+                ("max_norm", C.c_float), ("adamw", C.c_int32), ("step", C.c_int32), ("zero_grad", C.c_int32)]
 
 
 GRAD_NORM_SCRATCH = 1184

@@ -50,4 +50,4 @@ def test_chunk_rows_cover_a_tensor_exactly():
     assert rows == [(16, 32, 48, 64, 80, 5)]
     # struct mirrors stay in step with include/mdm_b200.h
     import ctypes as C
-    assert C.sizeof(optim.OptChunk) == 48 and C.sizeof(optim.AdamCfg) == 44
+    assert C.sizeof(optim.OptChunk) == 48 and C.sizeof(optim.AdamCfg) == 72
