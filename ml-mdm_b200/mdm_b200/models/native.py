@@ -216,7 +216,7 @@ class NativeNet:
         self.grad_arena = torch.zeros(total, device=dev, dtype=torch.float32)
         self.arena_zeroed = True
         off = 0
-        self.params, self.grad_views, self.param_names, self.offsets = [], [], [], []
+        self.params, self.param_names, self.offsets = [], [], []
         # Arena layout: registration order at first; optimize_arena_layout() re-sorts it by how late each
         # gradient becomes final so that mdm_net_set_grad_ready can report it from the top down.
         if self.order is not None:
@@ -233,7 +233,6 @@ class NativeNet:
             _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
                                                    C.c_void_p(g.data_ptr())), "bind")
             self.params.append(p)
-            self.grad_views.append(g)
         self.sig = sig
         self.versions = None
 
@@ -314,7 +313,7 @@ class NativeNet:
         aliased = any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params)
         if aliased:
             arena = torch.zeros_like(self.grad_arena)
-            views = [arena[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+            views = self._views(arena)
             for k, p, g in zip(self.param_names, self.params, views):
                 _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
                                                        C.c_void_p(g.data_ptr())), "bind")
@@ -323,12 +322,19 @@ class NativeNet:
             if not self.arena_zeroed:  # the fused optimiser sweep (optim.FusedAdam) leaves it zeroed
                 arena.zero_()
             self.arena_zeroed = False
-            views = self.grad_views
+            views = self._views(arena)
         st = torch.cuda.current_stream().cuda_stream
         self.active_arena = arena  # what a gradient-ready callback (parallel.GradientOverlap) indexes into
         _lib.check(self.lib.mdm_net_backward(self.handle, C.byref(gio), C.c_void_p(st)), "mdm_net_backward")
         self._keep = None
         return [g if p.requires_grad else None for p, g in zip(self.params, views)]
+
+    def _views(self, arena):
+        """Fresh per-parameter views of `arena` for autograd. They must not be referenced anywhere else:
+        AccumulateGrad adopts an incoming gradient as `.grad` only when it holds the sole reference and clones
+        it otherwise, and the flat-arena paths (one NCCL all-reduce, GradientOverlap, FusedAdam) rely on `.grad`
+        aliasing the arena."""
+        return [arena[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
 
     def optimize_arena_layout(self):
         """Re-sort the gradient arena by the order gradients become final in backward (learned by the

@@ -169,12 +169,16 @@ def test_grad_ready_ranges_are_final(kind):
     assert len(snaps) >= 3, "no gradient range was reported during the second backward"
     arena = native.grad_arena
     covered = 0
-    prev_lo = arena.numel()
+    prev_lo = max(off + p.numel() for p, off in zip(native.params, native.offsets))  # end of the last gradient
+    top = prev_lo
     for a, b, snap in snaps:
         assert b == prev_lo, "ranges must tile the arena from the top down without gaps or overlap"
         prev_lo = a
         covered += b - a
         assert torch.equal(snap, arena[a:b]), f"gradient range [{a},{b}) changed after it was reported final"
-    assert prev_lo == 0 and covered == arena.numel()
+    assert prev_lo == 0 and covered == top
+    # gradients handed to autograd alias the arena (adopted, not cloned)
+    lo_b, hi_b = arena.data_ptr(), arena.data_ptr() + 4 * arena.numel()
+    assert all(lo_b <= p.grad.data_ptr() < hi_b for p in model.parameters())
     # and the step still produced non-trivial gradients
     assert float(arena.abs().max()) > 0
