@@ -141,6 +141,14 @@ def _pad(n):
     return (n + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
 
 
+def arena_views(arena, params, offsets):
+    """Fresh per-parameter views of a flat gradient arena for autograd. They must not be referenced anywhere
+    else: AccumulateGrad adopts an incoming gradient as `.grad` only when it holds the sole reference and clones
+    it otherwise, and the flat-arena paths (one NCCL all-reduce, GradientOverlap, FusedAdam) rely on `.grad`
+    aliasing the arena."""
+    return [arena[off:off + p.numel()].view_as(p) for p, off in zip(params, offsets)]
+
+
 class NativeNet:
     def __init__(self, module):
         self.module = module
@@ -330,11 +338,7 @@ class NativeNet:
         return [g if p.requires_grad else None for p, g in zip(self.params, views)]
 
     def _views(self, arena):
-        """Fresh per-parameter views of `arena` for autograd. They must not be referenced anywhere else:
-        AccumulateGrad adopts an incoming gradient as `.grad` only when it holds the sole reference and clones
-        it otherwise, and the flat-arena paths (one NCCL all-reduce, GradientOverlap, FusedAdam) rely on `.grad`
-        aliasing the arena."""
-        return [arena[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        return arena_views(arena, self.params, self.offsets)
 
     def optimize_arena_layout(self):
         """Re-sort the gradient arena by the order gradients become final in backward (learned by the
