@@ -33,9 +33,12 @@ def allreduce_gradients(module, group=None, average=True):
         return 0
     arena = flat_grads(module)
     if arena is not None:
-        dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            arena.div_(world)
+        if average and arena.is_cuda:   # NCCL averages in the collective: no extra 1.8 GB pass
+            dist.all_reduce(arena, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                arena.div_(world)
         return 1
     bucket = [p.grad for p in module.parameters() if p.grad is not None]
     return allreduce_tensors(bucket, group=group, average=average)
