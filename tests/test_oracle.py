@@ -171,3 +171,64 @@ def test_oracle_matches_live_reference_on_shipped_64_config():
         ref = model(x, t, lm, mask, {})
         out = net.forward(dict(model.state_dict()), x, t, lm, mask, {})
     close(out, ref, 1e-5)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not mounted (GPU box)")
+def test_oracle_matches_live_reference_on_shipped_256_config():
+    """cc12m_256x256 at full width (2-level nest, 476.6 M parameters), B=1, S=8: oracle vs the reference's
+    NestedUNet — pins the nesting adapters, the inner/outer skip wiring and the 4x resolution ratio at the real
+    channel widths (the tiny nested fixture pins them at toy widths)."""
+    torch.manual_seed(1)
+    y = rh.load_yaml("cc12m_256x256.yaml")
+    model, _ = rh.build(y["unet_config"], y["diffusion_config"], "nested_unet", 2048)
+    with torch.no_grad():
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.normal_(0, 0.02)
+    ucfg = copy.deepcopy(y["unet_config"])
+    ucfg["initialize_inner_with_pretrained"] = None
+    net = unet_ref.OracleNet(ns(ucfg), 2048)
+    xs = [torch.randn(1, 3, 256, 256), torch.randn(1, 3, 64, 64)]
+    t = torch.tensor([233])
+    lm = torch.randn(1, 8, 2048)
+    mask = torch.ones(1, 8)
+    with torch.no_grad():
+        ref = model(xs, t, lm, mask, {})
+        out = net.forward(dict(model.state_dict()), xs, t, lm, mask, {})
+    assert len(out) == len(ref) == 2
+    for o, r in zip(out, ref):
+        assert o.shape == r.shape
+        close(o, r, 1e-5)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not mounted (GPU box)")
+def test_oracle_matches_live_reference_on_shipped_1024_config():
+    """cc12m_1024x1024 at full width (3-level nest, 481 M parameters), B=1, S=4: oracle vs the reference."""
+    torch.manual_seed(2)
+    y = rh.load_yaml("cc12m_1024x1024.yaml")
+    model, _ = rh.build(y["unet_config"], y["diffusion_config"], "nested2_unet", 2048)
+    with torch.no_grad():
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.normal_(0, 0.02)
+
+    def strip(d):  # nested dicts: no pretrained initialisation anywhere
+        if isinstance(d, dict):
+            if "initialize_inner_with_pretrained" in d:
+                d["initialize_inner_with_pretrained"] = None
+            for v in d.values():
+                strip(v)
+        return d
+
+    net = unet_ref.OracleNet(ns(strip(copy.deepcopy(y["unet_config"]))), 2048)
+    xs = [torch.randn(1, 3, 1024, 1024), torch.randn(1, 3, 256, 256), torch.randn(1, 3, 64, 64)]
+    t = torch.tensor([77])
+    lm = torch.randn(1, 4, 2048)
+    mask = torch.ones(1, 4)
+    with torch.no_grad():
+        ref = model(xs, t, lm, mask, {})
+        out = net.forward(dict(model.state_dict()), xs, t, lm, mask, {})
+    assert len(out) == len(ref) == 3
+    for o, r in zip(out, ref):
+        assert o.shape == r.shape
+        close(o, r, 1e-5)
