@@ -147,6 +147,12 @@ typedef struct mdm_net_io {
   const float* micro_scale;         /* (batch,) fp32 or NULL => per-level default (unet.py:924) */
   float* out[MDM_MAX_LEVELS];       /* NCHW fp32 predictions, same shapes as x_t */
   int32_t save_for_backward;
+  /* Mixed-resolution batches (NestedDiffusionConfig.mixed_ratio, diffusion.py:262-274; nested_unet.py:180,
+   * 193-204,209): level l processes only the FIRST level_batch[l] samples (0 => batch). Must not decrease from
+   * outer to inner levels and the innermost level runs the whole batch; x_t[l] / out[l] / dout[l] then hold
+   * level_batch[l] samples. Where an outer level is narrower than its inner one the in_adapter output is
+   * zero-padded and only the leading rows of the out_adapter result are used, as in the reference. */
+  int32_t level_batch[MDM_MAX_LEVELS];
 } mdm_net_io;
 
 /* UNet.forward / NestedUNet.forward (unet.py:971-987). */

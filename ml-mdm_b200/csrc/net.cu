@@ -105,7 +105,13 @@ struct Net {
     float* nhwc = nullptr;  // [pix][out_ch]
     __half* d16 = nullptr;  // [pix][8] scaled gradient (filled by backward)
     int res = 0;
+    int batch = 0;
   } outs[MDM_MAX_LEVELS];
+  // samples level li processes (mixed-resolution batches run only a leading part of the batch on outer levels)
+  int level_batch(int li) const {
+    const int b = io->level_batch[li];
+    return b > 0 ? b : io->batch;
+  }
 
   ~Net() {
     for (void* p : persistent) cudaFree(p);
@@ -943,7 +949,11 @@ struct Net {
         unfold_ln_grads(dWf, dbf, kw.w, lw.w, lb.w, kw.g, lw.g, lb.g, 2 * C, cd, E.st);
         E.pool.release(dWf);
         E.pool.release(dbf);
-        if (cs.dxhat == nullptr) cs.dxhat = E.alloc<float>(crow * cd);
+        const bool whole = B == cs.B;  // a level that ran only part of the batch touches the leading rows only
+        if (cs.dxhat == nullptr) {
+          cs.dxhat = whole ? E.alloc<float>(crow * cd) : E.zeros_f32(static_cast<long long>(cs.B) * S * cd);
+          cs.dxhat_init = !whole;
+        }
         {
           Epi e;
           e.out_f32 = cs.dxhat;
@@ -1016,23 +1026,30 @@ struct Net {
   }
 
   // generic 3x3 stride-1 conv on an fp16 NHWC operand producing a new Act (+ optional residual)
+  // n_alloc > N: the Act holds n_alloc samples, the conv fills the first N and the rest is zero
+  // (nested_unet.py:200-204 pads the in_adapter output for the samples the outer level did not run)
   Act* conv_act(const std::string& wname, const std::string& bname, const __half* x16, int N, int H, int W, int Cin,
-                int Cout, const float* residual) {
+                int Cout, const float* residual, int n_alloc = 0) {
     Param &w = P(wname), &bb = P(bname);
-    Act* y = eng.new_act(N, H, W, Cout);
+    Act* y = eng.new_act(std::max(N, n_alloc), H, W, Cout);
     Epi e;
     e.bias = bb.w;
     e.residual = residual;
     e.out_f32 = y->p;
     eng.conv3x3_fwd(x16, Cin, N, H, W, Cin, w.w16, Cout, e);
+    if (n_alloc > N) {
+      const long long lead = static_cast<long long>(N) * H * W * Cout;
+      MDM_CUDA(cudaMemsetAsync(y->p + lead, 0, sizeof(float) * (y->numel() - lead), eng.st));
+    }
     return y;
   }
   // backward of conv_act: returns fp32 gradient w.r.t. the fp16 operand (caller releases)
-  float* conv_act_bwd(const std::string& wname, const std::string& bname, const __half* x16, Act* y, int Cin) {
+  float* conv_act_bwd(const std::string& wname, const std::string& bname, const __half* x16, Act* y, int Cin,
+                      int n_lead = 0) {
     Engine& E = eng;
     Param &w = P(wname), &bb = P(bname);
-    const int N = y->n, H = y->h, W = y->w, Cout = y->c;
-    const long long rows = y->rows();
+    const int N = n_lead > 0 ? n_lead : y->n, H = y->h, W = y->w, Cout = y->c;
+    const long long rows = static_cast<long long>(N) * H * W;
     __half* d16 = E.alloc<__half>(rows * Cout);
     cast_colsum(y->g, d16, rows, Cout, bb.g, inv_scale(), E.st);
     if (w.g != nullptr) {
@@ -1221,9 +1238,9 @@ struct Net {
   }
 
   // temb of one level (unet.py:939-943 / nested_unet.py:172-176) + the level's FiLM matrix
-  LevelStep* temb_fwd(const LevelSpec& L) {
+  LevelStep* temb_fwd(const LevelSpec& L, int B) {
     Engine& E = eng;
-    const int B = io->batch, td = L.c.temporal_dim, half = td / 8;
+    const int td = L.c.temporal_dim, half = td / 8;
     lsteps.emplace_back();
     LevelStep* ls = &lsteps.back();
     const long long n = static_cast<long long>(B) * td;
@@ -1263,8 +1280,8 @@ struct Net {
       embed_mlp_bwd(Lp->pre + "temb_layer1", Lp->pre + "temb_layer2", trec, dt, B, td);
       if (micro) embed_mlp_bwd(Lp->pre + "cond_layers.scale.0", Lp->pre + "cond_layers.scale.1", mrec, dt, B, td);
       if (cs.cemb != nullptr) {
-        if (cs.dcemb == nullptr) cs.dcemb = E.alloc<float>(n);
-        axpy_f32(cs.dcemb, dt, 1.f, n, cs.dcemb_init ? 1 : 0, E.st);
+        if (cs.dcemb == nullptr) cs.dcemb = E.zeros_f32(static_cast<long long>(cs.B) * td);  // whole batch
+        axpy_f32(cs.dcemb, dt, 1.f, n, 1, E.st);  // this level's leading rows
         cs.dcemb_init = true;
       }
       E.pool.release(dt);
@@ -1277,8 +1294,9 @@ struct Net {
   Act* level_fwd(int li, Act* x_feat) {
     Engine& E = eng;
     const LevelSpec& L = levels[li];
-    const int B = io->batch, R = io->res[li], C0 = L.c.channels[0];
-    LevelStep* ls = temb_fwd(L);
+    const int B = level_batch(li), R = io->res[li], C0 = L.c.channels[0];
+    MDM_CHECK(x_feat == nullptr || x_feat->n == B, "x_feat batch");
+    LevelStep* ls = temb_fwd(L, B);
     // conv_in (+ x_feat when nested)  (unet.py:867-874,946-950; nested_unet.py:184-188)
     float* inv_std = nullptr;
     if (li < cfg.num_levels - 1 && !L.c.skip_normalization) {
@@ -1344,14 +1362,16 @@ struct Net {
       MDM_CHECK(H == io->res[li + 1], "outer bottleneck resolution must equal the inner image size");
       __half* x16 = E.alloc<__half>(x->numel());
       cast_f32_to_f16(x->p, x16, x->numel(), E.st);
-      Act* xin = conv_act(L.pre + "in_adapter.weight", L.pre + "in_adapter.bias", x16, N, H, W, Co, Ci, nullptr);
+      const int Bin = level_batch(li + 1);  // >= N; the inner level's extra samples see a zero feature
+      MDM_CHECK(Bin >= N, "level_batch must not decrease from outer to inner levels");
+      Act* xin = conv_act(L.pre + "in_adapter.weight", L.pre + "in_adapter.bias", x16, N, H, W, Co, Ci, nullptr, Bin);
       Act* xo_in = x;
       if (E.training) {
         const LevelSpec* Lp = &L;
         E.tape.push_back([=]() {
           if (xin->g == nullptr) return;
           Engine& E = eng;
-          float* dx16 = conv_act_bwd(Lp->pre + "in_adapter.weight", Lp->pre + "in_adapter.bias", x16, xin, Co);
+          float* dx16 = conv_act_bwd(Lp->pre + "in_adapter.weight", Lp->pre + "in_adapter.bias", x16, xin, Co, N);
           int acc = 0;
           float* g = E.grad_buf(xo_in, &acc);
           axpy_f32(g, dx16, 1.f, xo_in->numel(), acc, E.st);
@@ -1362,8 +1382,11 @@ struct Net {
         E.pool.release(x16);
       }
       Act* feat = level_fwd(li + 1, xin);
-      __half* f16 = E.alloc<__half>(feat->numel());
-      cast_f32_to_f16(feat->p, f16, feat->numel(), E.st);
+      // out_adapter on the leading N samples only: the reference convolves all Bin and slices [:N] (nested_unet.py:208-209),
+      // so the dropped rows contribute neither to the output nor to any gradient
+      const long long lead = static_cast<long long>(N) * H * W * Ci;
+      __half* f16 = E.alloc<__half>(lead);
+      cast_f32_to_f16(feat->p, f16, lead, E.st);
       Act* xn = conv_act(L.pre + "out_adapter.weight", L.pre + "out_adapter.bias", f16, N, H, W, Ci, Co, x->p);
       if (E.training) {
         const LevelSpec* Lp = &L;
@@ -1373,7 +1396,9 @@ struct Net {
           float* df = conv_act_bwd(Lp->pre + "out_adapter.weight", Lp->pre + "out_adapter.bias", f16, xn, Ci);
           int acc = 0;
           float* g = E.grad_buf(feat, &acc);
-          axpy_f32(g, df, 1.f, feat->numel(), acc, E.st);
+          axpy_f32(g, df, 1.f, lead, acc, E.st);
+          if (!acc && feat->numel() > lead)
+            MDM_CUDA(cudaMemsetAsync(g + lead, 0, sizeof(float) * (feat->numel() - lead), E.st));
           E.pool.release(df);
           g = E.grad_buf(xo_in, &acc);
           axpy_f32(g, xn->g, 1.f, xo_in->numel(), acc, E.st);
@@ -1408,6 +1433,7 @@ struct Net {
       nhwc_to_nchw(o, oc, io->out[li], B, oc, HW, E.st);
       E.pool.release(o);
       outs[li].res = R;
+      outs[li].batch = B;
       if (E.training) {
         const LevelSpec* Lp = &L;
         OutRec* orec = &outs[li];
@@ -1455,7 +1481,9 @@ struct Net {
     io = io_;
     for (int l = 0; l < MDM_MAX_LEVELS; ++l) outs[l] = OutRec();
     MDM_CHECK(io->batch > 0, "batch");
+    MDM_CHECK(level_batch(cfg.num_levels - 1) == io->batch, "the innermost level runs the whole batch");
     for (int l = 0; l < cfg.num_levels; ++l) {
+      MDM_CHECK(level_batch(l) >= 1 && level_batch(l) <= io->batch, "level_batch out of range");
       MDM_CHECK(io->x_t[l] != nullptr && io->out[l] != nullptr, "missing x_t/out pointer");
       MDM_CHECK(io->res[l] % (1 << (cfg.levels[l].num_res - 1)) == 0, "resolution not divisible by the level's downsampling");
     }
@@ -1472,16 +1500,16 @@ struct Net {
     eng.st = st;
     // gradient scale from the largest |dout| (fp16 operands need the seed in range)
     MDM_CUDA(cudaMemsetAsync(eng.d_amax, 0, sizeof(float), st));
-    const int B = cs.B;
     for (int l = 0; l < cfg.num_levels; ++l) {
       if (gio->dout[l] == nullptr) continue;
-      const long long n = static_cast<long long>(B) * cfg.out_channels * outs[l].res * outs[l].res;
+      const long long n = static_cast<long long>(outs[l].batch) * cfg.out_channels * outs[l].res * outs[l].res;
       grad_amax(gio->dout[l], n, eng.d_amax, st);
     }
     grad_scale_finalize(eng.d_amax, eng.d_scale, eng.d_inv_scale, st);
     for (int l = 0; l < cfg.num_levels; ++l) {
       if (gio->dout[l] == nullptr) continue;
       const int HW = outs[l].res * outs[l].res;
+      const int B = outs[l].batch;
       outs[l].d16 = eng.alloc<__half>(static_cast<long long>(B) * HW * 8);
       nchw_to_nhwc_f16(gio->dout[l], eng.d_scale, outs[l].d16, 8, B, cfg.out_channels, HW, st);
     }

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) adam_ema_sweep_kernel(const mdm_opt_chunk
   if (s.max_norm > 0.f) {
     // clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1 (torch/nn/utils/clip_grad.py)
     const float coef = s.max_norm / (__ldg(norm) + 1e-6f);
-    clip = __fmul_rn(s.grad_scale, fminf(coef, 1.0f));
+    // torch.clamp(coef, max=1.0) propagates NaN (a NaN norm poisons every gradient, as in the reference); fminf would drop it
+    clip = __fmul_rn(s.grad_scale, coef < 1.0f ? coef : (coef != coef ? coef : 1.0f));
   }
   const long long n = c.n;
   const bool vec = ((reinterpret_cast<uintptr_t>(c.p) | reinterpret_cast<uintptr_t>(c.g) |

@@ -21,6 +21,10 @@ from .config import DiffusionConfig, NestedDiffusionConfig  # noqa: F401
 from .samplers import _f32c, _ptr, _stream
 
 
+def _off(t, nbytes):
+    return C.c_void_p(t.data_ptr() + nbytes) if t is not None else None
+
+
 class _LossFn(torch.autograd.Function):
     """loss(B,) = sum_levels w_l * mean_chw (pred_for_training_l - target_l)^2 and its gradient w.r.t.
     the model outputs (diffusion.py:160-168, 367-386)."""
@@ -42,10 +46,17 @@ class _LossFn(torch.autograd.Function):
             p = torch.empty_like(mo) if want else None
             tg = torch.empty_like(mo) if want else None
             if lv["weight"] != 0.0 or want:
-                _lib.check(lib.mdm_loss_fwd(_ptr(mo), _ptr(xt), _ptr(x), _ptr(eps), _ptr(time), _ptr(lv["table"]),
-                                            spec["ptype"], spec["ltype"], C.c_float(lv["image_div"]),
-                                            C.c_float(lv["weight"]), _ptr(loss), _ptr(p), _ptr(tg), B,
-                                            C.c_int64(per), _stream()), "mdm_loss_fwd")
+                valid = min(int(lv.get("valid", B)), B)
+                # rows [0, valid) carry the loss; the rest (mixed-resolution batches) only produce pred / target
+                for lo, hi, wgt in ((0, valid, lv["weight"]), (valid, B, 0.0)):
+                    if hi <= lo or (wgt == 0.0 and not want):
+                        continue
+                    o4, o1 = lo * per * 4, lo * 4
+                    _lib.check(lib.mdm_loss_fwd(_off(mo, o4), _off(xt, o4), _off(x, o4), _off(eps, o4),
+                                                _off(time, lo * 8), _ptr(lv["table"]), spec["ptype"], spec["ltype"],
+                                                C.c_float(lv["image_div"]), C.c_float(wgt), _off(loss, o1),
+                                                _off(p, o4), _off(tg, o4), hi - lo, C.c_int64(per), _stream()),
+                               "mdm_loss_fwd")
             preds.append(p)
             tgts.append(tg)
             saved += [mo, xt, x, eps]
@@ -68,10 +79,13 @@ class _LossFn(torch.autograd.Function):
                 grads += [torch.zeros_like(mo), None, None, None]
                 continue
             B = mo.shape[0]
+            valid = min(int(lv.get("valid", B)), B)
             d = torch.empty_like(mo)
+            if valid < B:
+                d[valid:].zero_()
             _lib.check(lib.mdm_loss_bwd(_ptr(mo), _ptr(xt), _ptr(x), _ptr(eps), _ptr(time), _ptr(lv["table"]),
                                         spec["ptype"], spec["ltype"], C.c_float(lv["image_div"]),
-                                        C.c_float(lv["weight"]), _ptr(dloss), _ptr(d), B,
+                                        C.c_float(lv["weight"]), _ptr(dloss), _ptr(d), valid,
                                         C.c_int64(mo.numel() // B), _stream()), "mdm_loss_bwd")
             grads += [d, None, None, None]
         return (None, None) + tuple(grads)
@@ -112,12 +126,18 @@ class NestedModel(Model):
     """diffusion.py:251-292 with no_use_residual=True (the only working mode of the reference)."""
 
     def forward(self, x_t: List[torch.Tensor], times, lm_outputs, lm_mask, micros={}, mixed_ratio=None):
-        if mixed_ratio is not None:
-            raise NotImplementedError("mixed_ratio batches (partial high-resolution batches) are not built yet")
         if not self.diffusion_config.no_use_residual:
             raise NotImplementedError("NestedModel residual mode references an undefined variable in the reference "
                                       "(diffusion.py:288); shipped configs set no_use_residual: true")
-        return self.vision_model(x_t, times, lm_outputs, lm_mask, micros)
+        if mixed_ratio is None:
+            return self.vision_model(x_t, times, lm_outputs, lm_mask, micros)
+        # diffusion.py:262-274: each level sees only a leading part of the batch (the engine slices temb /
+        # conditioning and zero-pads the in_adapter output itself); predictions are zero-padded back to the batch
+        batch_size = x_t[0].size(0)
+        x_t = [x[: int(m * x.size(0))] for x, m in zip(x_t, mixed_ratio)]
+        p_t = self.vision_model(x_t, times, lm_outputs, lm_mask, micros)
+        return [torch.cat([p, p.new_zeros(batch_size - p.size(0), *p.size()[1:])], 0) if p.size(0) < batch_size else p
+                for p in p_t]
 
 
 class Diffusion(nn.Module):
@@ -195,8 +215,9 @@ class NestedDiffusion(Diffusion):
         self.model.set_sampler(self.sampler)
         self._config = diffusion_config
         self.mixed_ratio = None
-        if getattr(self._config, "mixed_ratio", None):
-            raise NotImplementedError("mixed_ratio batches are not built yet (SURVEY.md 8f rank 4)")
+        if getattr(self._config, "mixed_ratio", None):  # diffusion.py:309-313, e.g. '2:1' -> [2/3, 1]
+            mr = np.cumsum(np.asarray([float(x) for x in str(self._config.mixed_ratio).split(":")]))
+            self.mixed_ratio = mr / mr[-1]
 
     @staticmethod
     def avg_pool(x, r):
@@ -237,9 +258,14 @@ class NestedDiffusion(Diffusion):
         levels, flat = [], []
         for i, (p, xt, x, e, s) in enumerate(zip(p_t, x_t, imgs, epss, scales)):
             active = (i == 0) or self._config.use_double_loss
-            levels.append(dict(table=self.sampler.level_table(s, images.device),
-                               image_div=self.sampler.level_image_div(s), weight=w[i] if active else 0.0,
-                               want_outputs=(i == 0)))
+            lv = dict(table=self.sampler.level_table(s, images.device),
+                      image_div=self.sampler.level_image_div(s), weight=w[i] if active else 0.0,
+                      want_outputs=(i == 0))
+            if self.mixed_ratio is not None and active:
+                # diffusion.py:378-382: loss_ / mixed_ratio[i], rows beyond int(mixed_ratio[i] * B) discarded
+                lv["weight"] = w[i] / float(self.mixed_ratio[i])
+                lv["valid"] = int(self.mixed_ratio[i] * p.shape[0])
+            levels.append(lv)
             flat += [p, xt, x, e]
         loss, pred0, tgt0 = _LossFn.apply(dict(ptype=ptype, ltype=ltype, levels=levels), time, *flat)
         return loss, time, x_t[0], pred0, tgt0, weights

@@ -54,6 +54,7 @@ class NetIO(C.Structure):
         ("micro_scale", C.c_void_p),
         ("out", C.c_void_p * MAX_LEVELS),
         ("save_for_backward", C.c_int32),
+        ("level_batch", C.c_int32 * MAX_LEVELS),
     ]
 
 
@@ -216,7 +217,7 @@ class NativeNet:
                                     "There is no CPU path.")
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.MdmError(f"parameter {k} must be contiguous fp32")
-        sig = tuple(p.data_ptr() for _, p in plist)
+        sig = tuple(p.data_ptr() for _, p in plist) + tuple(p.requires_grad for _, p in plist)
         if sig == self.sig:
             return
         dev = plist[0][1].device
@@ -238,8 +239,11 @@ class NativeNet:
             self.offsets.append(off)
             g = self.grad_arena[off:off + p.numel()].view_as(p)
             off += _pad(p.numel())
+            # frozen parameters (requires_grad=False, e.g. freeze_inner_unet, nested_unet.py:147-150) get no
+            # gradient pointer: the engine skips their weight gradients, their arena slot stays zero and the
+            # global norm / optimiser sweep never see them (clip_grad_norm_ ignores them in the reference too)
             _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
-                                                   C.c_void_p(g.data_ptr())), "bind")
+                                                   C.c_void_p(g.data_ptr()) if p.requires_grad else None), "bind")
             self.params.append(p)
         self.sig = sig
         self.versions = None
@@ -263,7 +267,7 @@ class NativeNet:
     def _forward(self, xs, times, lm, mask, micro, save):
         self._sync_weights()
         io = NetIO()
-        B = xs[0].shape[0]
+        B = xs[-1].shape[0]  # the innermost level always runs the whole batch (nested_unet.py:180,200-204)
         io.batch = B
         keep = []
 
@@ -279,7 +283,12 @@ class NativeNet:
             if not x.is_cuda:
                 raise _lib.MdmError("inputs must be CUDA tensors")
             x = f32(x)
-            assert x.shape[0] == B and x.shape[2] == x.shape[3], "mixed-resolution batches are not built"
+            if x.shape[2] != x.shape[3]:
+                raise _lib.MdmError("square images only")
+            if not (1 <= x.shape[0] <= B) or (i > 0 and x.shape[0] < xs[i - 1].shape[0]):
+                raise _lib.MdmError("mixed-resolution batches: each level runs a leading part of the batch and inner "
+                                    f"levels at least as many samples as outer ones; got {[t.shape[0] for t in xs]}")
+            io.level_batch[i] = x.shape[0]
             io.res[i] = x.shape[2]
             io.x_t[i] = x.data_ptr()
             o = torch.empty_like(x)
@@ -324,7 +333,7 @@ class NativeNet:
             views = self._views(arena)
             for k, p, g in zip(self.param_names, self.params, views):
                 _lib.check(self.lib.mdm_net_bind_param(self.handle, k.encode(), C.c_void_p(p.data_ptr()),
-                                                       C.c_void_p(g.data_ptr())), "bind")
+                                                       C.c_void_p(g.data_ptr()) if p.requires_grad else None), "bind")
             self.sig = None  # rebinding to the persistent arena happens at the next forward
         else:
             if not self.arena_zeroed:  # the fused optimiser sweep (optim.FusedAdam) leaves it zeroed

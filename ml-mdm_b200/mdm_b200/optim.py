@@ -109,6 +109,15 @@ class FusedAdam(torch.optim.Optimizer):
             self._norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self._sig = sig
 
+    def load_state_dict(self, state_dict):
+        """torch's Adam layout in, fused state out: the step counter continues from the loaded `step` (bias
+        corrections 1 - beta^t stay consistent with the loaded moments) and the chunk table is rebuilt so the
+        kernel reads the loaded exp_avg / exp_avg_sq rather than its previous arena-shaped copies."""
+        super().load_state_dict(state_dict)
+        steps = [float(st["step"]) for st in self.state.values() if "step" in st]
+        self.steps = int(max(steps)) if steps else 0
+        self._sig = None
+
     # ------------------------------------------------------------------ step
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm=None, ema_model=None, grad_scale=1.0, zero_grad=True):
@@ -146,6 +155,12 @@ class FusedAdam(torch.optim.Optimizer):
         for p in native.params:
             self.state[p]["step"] = torch.tensor(float(self.steps))
         native.versions = None            # fp32 masters changed in place: fp16 operand copies are rebuilt next forward
+        if ema_model is not None:
+            # the sweep wrote the EMA parameters through raw pointers too (their torch ._version did not move):
+            # an engine already built for the EMA module must repack its fp16 operands before its next forward
+            ema_native = getattr(ema_model.module, "_native", None)
+            if ema_native is not None:
+                ema_native.versions = None
         if zero_grad:
             native.arena_zeroed = True    # the next backward skips its 1.8 GB memset
         return None

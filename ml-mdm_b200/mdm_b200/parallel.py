@@ -33,7 +33,7 @@ def allreduce_gradients(module, group=None, average=True):
         return 0
     arena = flat_grads(module)
     if arena is not None:
-        if average and arena.is_cuda:   # NCCL averages in the collective: no extra 1.8 GB pass
+        if average and dist.get_backend(group) == "nccl":   # NCCL averages in the collective: no extra 1.8 GB pass
             dist.all_reduce(arena, op=dist.ReduceOp.AVG, group=group)
         else:
             dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=group)
@@ -77,7 +77,7 @@ class GradientOverlap:
 
     def _reduce(self, t, async_op):
         world = dist.get_world_size(self.group)
-        if self.average and t.is_cuda:
+        if self.average and dist.get_backend(self.group) == "nccl":
             return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
         w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         if self.average:

@@ -142,9 +142,18 @@ def nested_pyramid(images, ratios):
     return out
 
 
+def mixed_ratio_fractions(spec):
+    """NestedDiffusion.__init__ (diffusion.py:308-313): '2:1' -> cumulative fractions [2/3, 1]."""
+    if not spec:
+        return None
+    mr = np.cumsum(np.asarray([float(x) for x in str(spec).split(":")]))
+    return mr / mr[-1]
+
+
 def training_loss(net, P, images, eps_list, time, lm, mask, gammas, scales, ptype, ltype, shifted, power,
-                  weights=None, double_loss=True):
-    """Base (scales == [1]) or nested get_loss given the noise tensors. Returns (loss(B,), x_t list, outs)."""
+                  weights=None, double_loss=True, mixed_ratio=None):
+    """Base (scales == [1]) or nested get_loss given the noise tensors. Returns (loss(B,), x_t list, outs).
+    mixed_ratio: cumulative fractions per level (diffusion.py:262-274, 378-382)."""
     nested = len(scales) > 1
     ratios = [scales[0] // s for s in scales]
     imgs = nested_pyramid(images, ratios) if nested else [images]
@@ -152,14 +161,25 @@ def training_loss(net, P, images, eps_list, time, lm, mask, gammas, scales, ptyp
     gs = [shift_table(g_base, s, power) if (nested and shifted) else g_base for s in scales]
     divs = [1.0 if (not nested or shifted) else float(s) for s in scales]
     x_t = [q_sample(x / d if d != 1.0 else x, e, g) for x, e, g, d in zip(imgs, eps_list, gs, divs)]
-    outs = net.forward(P, x_t if nested else x_t[0], time, lm, mask, {})
+    B = images.shape[0]
+    x_in = x_t
+    if mixed_ratio is not None:  # NestedModel.forward: leading part of the batch per level, zero-padded predictions
+        x_in = [x[: int(m * x.size(0))] for x, m in zip(x_t, mixed_ratio)]
+    outs = net.forward(P, x_in if nested else x_in[0], time, lm, mask, {})
     outs = list(outs) if nested else [outs]
+    if mixed_ratio is not None:
+        outs = [torch.cat([p, p.new_zeros(B - p.size(0), *p.size()[1:])], 0) for p in outs]
     w = weights or [1.0] * len(scales)
     loss = 0
     for i in range(len(scales)):
         if i == 0 or double_loss:
             li, _, _ = level_loss(outs[i], x_t[i], imgs[i] / divs[i] if divs[i] != 1.0 else imgs[i], eps_list[i], gs[i],
                                   ptype, ltype)
+            if mixed_ratio is not None:
+                li = li / float(mixed_ratio[i])
+                keep = torch.zeros_like(li)
+                keep[: int(mixed_ratio[i] * B)] = 1
+                li = li * keep
             loss = loss + li * w[i]
     return loss, x_t, outs
 

@@ -142,3 +142,44 @@ def test_pipeline_sample_entry_point_shapes():
                       num_inference_steps=3, ddim_eta=1.0, resample_steps=True, yield_output=True, output_inner=True)
     frames = list(gen)
     assert len(frames) == 4 and frames[-1].shape == (2, 3, 32, 64)
+
+
+def test_get_loss_mixed_ratio_batches():
+    """NestedDiffusionConfig.mixed_ratio='2:1' (set by the shipped cc12m_256x256.yaml:108): the high-resolution level
+    runs only the leading int(2/3 B) samples inside the engine (mdm_net_io.level_batch), predictions are zero-padded,
+    the loss is rescaled and masked. Oracle: oracle.diffusion_ref.training_loss(mixed_ratio=...) -- itself pinned
+    against the live reference in tests/test_oracle.py."""
+    B = 3
+    model, oracle, sd = nc.build("nested")
+    d = copy.deepcopy(tc.TINY_NESTED_DIFFUSION)
+    d["mixed_ratio"] = "2:1"
+    pipe = NestedDiffusion(model, mc.diffusion_config_from_dict(d, True)).to("cuda")
+    assert pipe.mixed_ratio is not None and int(pipe.mixed_ratio[0] * B) == 2
+    x, t, lm, mask = tc.seeded_inputs(3, B, 32, 6, nlevels=2)
+    images = x[0].clamp(-1, 1)
+    torch.manual_seed(1234)
+    pipe.train()
+    loss, time, x_t, pred, tgt, w = pipe.get_loss({"images": images.cuda(), "lm_outputs": lm.cuda(), "lm_mask": mask.cuda()})
+    loss.mean().backward()
+    assert x_t.shape[0] == pred.shape[0] == tgt.shape[0] == B
+    torch.manual_seed(1234)
+    time_r = torch.randint(0, 1000, (B,), device="cuda")
+    eps = [torch.randn_like(images.cuda()), torch.empty(B, 3, 8, 8, device="cuda").normal_()]
+    assert torch.equal(time_r, time)
+    P = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    gam = dref.gammas_f32("DEEPFLOYD", 1000)
+    mr = dref.mixed_ratio_fractions("2:1")
+    oloss, ox_t, _ = dref.training_loss(oracle, P, images.double(), [e.cpu().double() for e in eps], time.cpu(), lm.double(),
+                                        mask.double(), gam, [4, 1], dref.V_PREDICTION, dref.DDPM, shifted=True, power=1,
+                                        mixed_ratio=mr)
+    oloss.mean().backward()
+    assert nc.rel(loss.detach().cpu().double(), oloss.detach()) <= 5e-3
+    mags = sorted(float(P[k].grad.abs().max()) for k in P)
+    floor = 1e-2 * mags[len(mags) // 2]
+    bad = {}
+    for k, p in pipe.get_model().vision_model.named_parameters():
+        ref = P[k].grad
+        e = float((p.grad.cpu().double() - ref).abs().max() / max(float(ref.abs().max()), floor))
+        if not e <= 3e-2:
+            bad[k] = e
+    assert not bad, bad

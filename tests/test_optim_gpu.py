@@ -132,3 +132,112 @@ def test_fused_adam_on_tiny_unet_matches_separate_calls():
     # and the engine picks the updated weights up: a third forward differs from the first
     out3 = model_a(x, t, lm, mask, {})
     assert float((out3 - out).abs().max()) > 0
+
+
+def _tiny(kind="unet"):
+    import net_cases as nc
+    import tiny_configs as tc
+    nlev = 1 if kind == "unet" else 2
+    model, _, _ = nc.build(kind)
+    model = model.cuda()
+    x, t, lm, mask = tc.seeded_inputs(3, 2, 16 if nlev == 1 else 32, 6, nlevels=nlev)
+    xs = x.cuda() if nlev == 1 else [xi.cuda() for xi in x]
+    return model, xs, t.cuda(), lm.cuda(), mask.cuda()
+
+
+def _loss(model, xs, t, lm, mask):
+    out = model(xs, t, lm, mask, {})
+    outs = list(out) if isinstance(out, (list, tuple)) else [out]
+    return sum((o ** 2).mean() for o in outs)
+
+
+def test_frozen_inner_unet_gradients_stay_out_of_norm_and_sweep():
+    """freeze_inner_unet (nested_unet.py:147-150) sets requires_grad=False on the inner U-Net: the engine must not
+    accumulate those gradients (they would never be zeroed by the sweep, inflate the global norm step after step and
+    drive the clip coefficient to 0), and the norm must equal clip_grad_norm_'s over the trainable parameters."""
+    model, xs, t, lm, mask = _tiny("nested")
+    for p in model.inner_unet.parameters():
+        p.requires_grad_(False)
+    frozen = {k: v.detach().clone() for k, v in model.inner_unet.state_dict().items()}
+    opt = optim.FusedAdam(model, lr=1e-3)
+    norms = []
+    for step in range(3):
+        _loss(model, xs, t, lm, mask).backward()
+        assert all(p.grad is None for p in model.inner_unet.parameters())
+        ref = torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 1e9)
+        native = model.native()
+        assert float(native.grad_arena.abs().max()) > 0
+        opt.step(max_grad_norm=1e9)
+        torch.cuda.synchronize()
+        assert abs(float(opt.last_grad_norm) - float(ref)) <= 1e-5 * float(ref)
+        assert float(native.grad_arena.abs().max()) == 0.0, "arena (frozen slots included) must be zero after the sweep"
+        norms.append(float(ref))
+        opt.zero_grad()
+    for k, v in model.inner_unet.state_dict().items():
+        assert torch.equal(v, frozen[k]), f"frozen parameter {k} moved"
+    assert norms[2] < 10 * norms[0]
+
+
+def test_ema_engine_sees_fused_updates():
+    """The sweep writes EMA parameters through raw pointers; an engine already built for the EMA module has to repack
+    its fp16 operand copies (ModelEma consumers sample from ema.module between updates)."""
+    model, xs, t, lm, mask = _tiny("unet")
+    ema = _Ema(model, 0.5, 0)
+    opt = optim.FusedAdam(model, lr=5e-2)
+    with torch.no_grad():
+        e0 = ema.module(xs, t, lm, mask, {}).clone()     # builds + caches the EMA module's engine
+    for _ in range(2):
+        _loss(model, xs, t, lm, mask).backward()
+        opt.step(max_grad_norm=1.0, ema_model=ema)
+        opt.zero_grad()
+    with torch.no_grad():
+        e1 = ema.module(xs, t, lm, mask, {})
+        fresh = copy.deepcopy(ema.module)               # no cached engine: packs from the current fp32 values
+        e2 = fresh(xs, t, lm, mask, {})
+    assert float((e1 - e0).abs().max()) > 0, "EMA forward still uses the weights packed before the updates"
+    assert torch.equal(e1, e2)
+
+
+def test_fused_adam_state_dict_round_trip_matches_torch_adam():
+    """save -> load -> step: bias corrections continue from the loaded step and the loaded moments are the ones used
+    (torch.optim.Adam on a copy, fed the same gradients, is the reference)."""
+    model_a, xs, t, lm, mask = _tiny("unet")
+    model_b = copy.deepcopy(model_a)
+    opt_a = optim.FusedAdam(model_a, lr=2e-3)
+    opt_b = torch.optim.Adam(model_b.parameters(), lr=2e-3, eps=1e-8)
+
+    def both_step(oa):
+        _loss(model_a, xs, t, lm, mask).backward()
+        for pa, pb in zip(model_a.parameters(), model_b.parameters()):
+            pb.grad = pa.grad.detach().clone()
+        opt_b.step()
+        opt_b.zero_grad()
+        oa.step()
+        oa.zero_grad()
+
+    for _ in range(3):
+        both_step(opt_a)
+    sd = copy.deepcopy(opt_a.state_dict())
+    # (a) a brand-new optimizer that loads the state; (b) the same optimizer re-loading after having stepped
+    opt_new = optim.FusedAdam(model_a, lr=2e-3)
+    opt_new.load_state_dict(sd)
+    assert opt_new.steps == 3
+    both_step(opt_new)
+    torch.cuda.synchronize()
+    for (k, a), (_, b) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
+        assert close(a, b.cpu()), f"{k}: {float((a - b).abs().max()):.3e}"
+    assert float(opt_new.state_dict()["state"][0]["step"]) == 4.0
+    sb = opt_b.state_dict()["state"]
+    for i, st in opt_new.state_dict()["state"].items():
+        assert close(st["exp_avg"], sb[i]["exp_avg"].cpu()) and close(st["exp_avg_sq"], sb[i]["exp_avg_sq"].cpu())
+    sd4 = copy.deepcopy(opt_new.state_dict())
+    both_step(opt_new)                 # moves on to step 5 ...
+    opt_new.load_state_dict(sd4)       # ... and is rolled back to the state after step 4
+    assert opt_new.steps == 4
+    m0 = opt_new.state_dict()["state"][0]["exp_avg"].clone()
+    _loss(model_a, xs, t, lm, mask).backward()
+    g0 = next(iter(model_a.parameters())).grad.detach().clone()
+    opt_new.step()
+    torch.cuda.synchronize()
+    m1 = opt_new.state_dict()["state"][0]["exp_avg"]
+    assert close(m1, (0.9 * m0 + 0.1 * g0).cpu()), "loaded exp_avg was not the one the kernel used"

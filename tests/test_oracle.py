@@ -232,3 +232,43 @@ def test_oracle_matches_live_reference_on_shipped_1024_config():
     for o, r in zip(out, ref):
         assert o.shape == r.shape
         close(o, r, 1e-5)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not mounted (GPU box)")
+def test_oracle_mixed_ratio_loss_matches_live_reference():
+    """NestedDiffusion.get_loss with mixed_ratio='2:1' (what configs/models/cc12m_256x256.yaml:108 sets): only the
+    leading int(2/3 * B) samples run the high-resolution level, predictions are zero-padded, the per-level loss is
+    divided by the fraction and masked (diffusion.py:262-274, 378-382; nested_unet.py:180,193-204,209). The oracle
+    replays the reference's CPU generator draws; loss and every gradient are compared."""
+    B = 3
+    dcfg = copy.deepcopy(tc.TINY_NESTED_DIFFUSION)
+    dcfg["mixed_ratio"] = "2:1"
+    ucfg = copy.deepcopy(tc.TINY_NESTED)
+    model, pipe = rh.build(ucfg, dcfg, "nested_unet", tc.LM_DIM)
+    sd = tc.seeded_state_dict(model.state_dict(), 7)
+    model.load_state_dict(sd)
+    x, t, lm, mask = tc.seeded_inputs(3, B, 32, 6, nlevels=2)
+    images = x[0].clamp(-1, 1)
+    torch.manual_seed(4321)
+    pipe.train()
+    loss, time, x_t, pred, tgt, _ = pipe.get_loss({"images": images, "lm_outputs": lm, "lm_mask": mask})
+    loss.mean().backward()
+    torch.manual_seed(4321)
+    time_r = torch.randint(0, 1000, (B,))
+    eps = [torch.randn_like(images), None]
+    eps[1] = torch.empty(B, 3, 8, 8).normal_()
+    assert torch.equal(time_r, time)
+    ocfg = copy.deepcopy(tc.TINY_NESTED)
+    ocfg["initialize_inner_with_pretrained"] = None
+    net = unet_ref.OracleNet(ns(ocfg), tc.LM_DIM)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    gam = dref.gammas_f32("DEEPFLOYD", 1000)
+    mr = dref.mixed_ratio_fractions("2:1")
+    assert int(mr[0] * B) == 2 and mr[1] == 1.0
+    oloss, ox_t, _ = dref.training_loss(net, P, images, eps, time, lm, mask, gam, [4, 1], dref.V_PREDICTION, dref.DDPM,
+                                        shifted=True, power=1, mixed_ratio=mr)
+    close(ox_t[0], x_t, 1e-6)
+    close(oloss, loss.detach())
+    oloss.mean().backward()
+    for k, p in model.named_parameters():
+        close(P[k].grad, p.grad, 2e-4)

@@ -91,13 +91,50 @@ def test_train_batch_mirrors_reference_control_flow(weighted):
     assert ea.counter == eb.counter
 
 
-def test_train_batch_rejects_fp16_flag():
+def _run_fp16(train_batch, ModelEma):
+    """args.fp16 branch (trainer.py:29-61) with a disabled GradScaler (bf16 autocast needs no loss scaling; CPU has no
+    CUDA scaler): loss_factor, pre-backward accumulation divide, NaN path without optimizer/scheduler step."""
+    pipe = _Pipe(True)
+    opt = torch.optim.Adam(pipe.model.vision_model.parameters(), lr=1e-2, eps=1e-8)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    ema = ModelEma(pipe.model.vision_model, decay=0.9, warmup_steps=1)
+    args = argparse.Namespace(fp16=True, gradient_clip_norm=0.05)
+    scaler = torch.amp.GradScaler("cuda", enabled=False)
+    g = torch.Generator().manual_seed(1)
+    out = []
+    for step in range(6):
+        s = {"x": torch.randn(4, 6, generator=g), "y": torch.randn(4, 6, generator=g), "w": torch.rand(4, generator=g)}
+        if step == 2:
+            s["x"][0, 0] = float("nan")
+        accumulate = step == 3
+        r = train_batch(pipe, s, opt, sched, None, args, grad_scaler=scaler, accumulate_gradient=accumulate,
+                        num_grad_accumulations=2 if step in (3, 4) else 1, ema_model=ema, loss_factor=0.5)
+        out.append((r[0], sched.get_last_lr()[0]))
+    return pipe, ema, out
+
+
+def test_train_batch_fp16_branch_mirrors_reference_control_flow():
+    if not rh.available():
+        pytest.skip("reference tree not mounted")
+    rh.load()
+    import warnings
+
+    from ml_mdm import trainer as ref_trainer
+    from ml_mdm.models.model_ema import ModelEma
+
     from mdm_b200 import trainer as my_trainer
-    pipe = _Pipe(False)
-    opt = torch.optim.Adam(pipe.parameters(), lr=1e-3)
-    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
-    with pytest.raises(NotImplementedError):
-        my_trainer.train_batch(pipe, {}, opt, sched, None, argparse.Namespace(fp16=True, gradient_clip_norm=1.0))
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # torch.cuda.amp.autocast on a CPU-only host warns and disables itself
+        pa, ea, oa = _run_fp16(ref_trainer.train_batch, ModelEma)
+    pb, eb, ob = _run_fp16(my_trainer.train_batch, ModelEma)
+    for (la, lra), (lb, lrb) in zip(oa, ob):
+        assert (la == lb or (la != la and lb != lb)) and lra == lrb
+    for (k, a), (_, b) in zip(pa.state_dict().items(), pb.state_dict().items()):
+        assert torch.equal(a, b), k
+    for (k, a), (_, b) in zip(ea.module.state_dict().items(), eb.module.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert ea.counter == eb.counter
 
 
 # ------------------------------------------------------------------ checkpoints
