@@ -155,6 +155,17 @@ typedef struct mdm_net_io {
   int32_t level_batch[MDM_MAX_LEVELS];
 } mdm_net_io;
 
+/* CUDA-graph execution of forward / backward (off by default). With it on, the first call with a given shape
+ * signature (batch, per-level batch, resolutions, tokens, mask/micro presence, save_for_backward) runs eagerly, the
+ * second is captured and later ones replay the captured graphs: inputs / output gradients are copied into static
+ * buffers, ONE graph launch runs the ~1-2.5 k kernels of the pass, outputs are copied out. Gradient-ready
+ * notifications (mdm_net_set_grad_ready) do not fire for replayed backwards. Rebinding parameters or gradients drops
+ * the recorded graphs. */
+int mdm_net_set_graph_mode(mdm_net* net, int enable);
+/* Number of graph launches issued by this library since load; kernels inside replayed graphs are included in
+ * mdm_launch_count(). */
+unsigned long long mdm_graph_launch_count(void);
+
 /* UNet.forward / NestedUNet.forward (unet.py:971-987). */
 int mdm_net_forward(mdm_net* net, const mdm_net_io* io, mdm_stream_t stream);
 
@@ -254,6 +265,18 @@ int mdm_loss_bwd(const float* model_out, const float* x_t, const float* x, const
 int mdm_sampler_step(const float* x_t, const float* pred, const float* noise, const float* gammas, int t_index,
                      int s_index, int prediction_type, int clip, float image_scale, int use_ddim, float ddim_eta,
                      int need_noise, float* x0_out, float* x_s_out, int64_t numel, mdm_stream_t stream);
+/* Dynamic thresholding, Sampler._threshold_sample / clip_sample (samplers.py:461-508), DYNAMIC = (0.995, 100),
+ * DYNAMIC_IF = (0.95, 1.5): bound[b] = clamp(quantile(|x0 * image_scale|, ratio), 1, max_value) over sample b's
+ * per_sample values, x0 recomputed from (x_t, pred, g = gammas[t_index]); exact order statistics (radix select) combined
+ * with torch.quantile's fp32 rank / lerp arithmetic. bound: (batch,) fp32, device. */
+int mdm_dynamic_threshold(const float* x_t, const float* pred, const float* gammas, int t_index, int prediction_type,
+                          float image_scale, float ratio, float max_value, float* bound, int batch, int64_t per_sample,
+                          mdm_stream_t stream);
+/* mdm_sampler_step with x0 = clamp(x0 * image_scale, -bound[b], bound[b]) / bound[b] / image_scale. */
+int mdm_sampler_step_dynamic(const float* x_t, const float* pred, const float* noise, const float* gammas, int t_index,
+                             int s_index, int prediction_type, const float* bound, float image_scale, int use_ddim,
+                             float ddim_eta, int need_noise, float* x0_out, float* x_s_out, int batch, int64_t per_sample,
+                             mdm_stream_t stream);
 /* classifier-free guidance: out = uncond + w * (cond - uncond)  (samplers.py:449-455) */
 int mdm_cfg_combine(const float* uncond, const float* cond, float guidance_scale, float* out, int64_t numel,
                     mdm_stream_t stream);

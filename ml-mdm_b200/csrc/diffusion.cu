@@ -20,6 +20,14 @@ __device__ __forceinline__ float x0_from_pred(int ptype, float xt, float pred, f
   if (ptype == PT_V) return xt * a - pred * c;
   return (xt - pred * c) / a;
 }
+// x0 * image_scale with one rounding per operation (no FMA contraction): the dynamic-threshold kernels rank these
+// values and the step kernel clips them -- both must see the same bits
+__device__ __forceinline__ float x0_scaled(int ptype, float xt, float pred, float a, float c, float image_scale) {
+  float x0;
+  if (ptype == PT_V) x0 = __fsub_rn(__fmul_rn(xt, a), __fmul_rn(pred, c));
+  else x0 = __fdiv_rn(__fsub_rn(xt, __fmul_rn(pred, c)), a);
+  return __fmul_rn(x0, image_scale);
+}
 __device__ __forceinline__ float pred_from_x0(int ltype, float xt, float x0, float a, float c) {
   // samplers.py:381-389
   if (ltype == PT_V) return (a * xt - x0) / c;
@@ -110,7 +118,7 @@ __global__ void sampler_step_kernel(const float* __restrict__ xt, const float* _
                                     const float* __restrict__ noise, const float* __restrict__ gammas, int t_idx,
                                     int s_idx, int ptype, int clip, float image_scale, int mode, float eta,
                                     int need_noise, float* __restrict__ x0_out, float* __restrict__ xs_out,
-                                    long long total) {
+                                    long long total, const float* __restrict__ bound, long long per) {
   const float g = gammas[t_idx], gl = gammas[s_idx];
   const float alpha = g / gl;
   const float beta = 1.0f - alpha;
@@ -120,8 +128,14 @@ __global__ void sampler_step_kernel(const float* __restrict__ xt, const float* _
   const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
   for (; k < total; k += gs) {
     const float x = xt[k];
-    float x0 = x0_from_pred(ptype, x, pred[k], a, c);
-    if (clip) x0 = fminf(fmaxf(x0 * image_scale, -1.0f), 1.0f) / image_scale;
+    float x0;
+    if (bound != nullptr) {  // dynamic thresholding (samplers.py:461-508): clamp(x0 s, -b, b) / b / s, b per sample
+      const float b = bound[k / per];
+      x0 = __fdiv_rn(__fdiv_rn(fminf(fmaxf(x0_scaled(ptype, x, pred[k], a, c, image_scale), -b), b), b), image_scale);
+    } else {
+      x0 = x0_from_pred(ptype, x, pred[k], a, c);
+      if (clip) x0 = fminf(fmaxf(x0 * image_scale, -1.0f), 1.0f) / image_scale;
+    }
     float xs;
     float bt = beta_tilde;
     int nn = need_noise;
@@ -140,6 +154,119 @@ __global__ void sampler_step_kernel(const float* __restrict__ xt, const float* _
     if (nn) xs = xs + sqrtf(bt) * noise[k];
     if (x0_out != nullptr) x0_out[k] = x0;
     xs_out[k] = xs;
+  }
+}
+
+
+// ---- dynamic thresholding (samplers.py:461-508): bound[b] = clamp(quantile(|x0 * image_scale|, q), 1, max_value) over
+// the C*H*W values of sample b, with torch.quantile's arithmetic: rank = q * (n - 1) in fp32, the two order statistics
+// at floor(rank) / ceil(rank), torch's lerp. The order statistics are EXACT: a 3-pass radix select (11 + 10 + 10 bits)
+// over the bit patterns of the non-negative floats, one CTA per sample, x0 recomputed from (x_t, pred) in every pass
+// so nothing is materialised.
+constexpr int DT_THREADS = 1024;
+
+__device__ __forceinline__ unsigned dt_key(int ptype, float xt, float pred, float a, float c, float image_scale) {
+  return __float_as_uint(fabsf(x0_scaled(ptype, xt, pred, a, c, image_scale)));
+}
+
+// Block-wide: which of the 2048 bins holds rank `r` (0-based among the counted elements)? Returns the bin and
+// rewrites r to the rank inside it. hist: 2048 counters in shared memory.
+__device__ unsigned dt_find_bin(const unsigned* hist, unsigned* r_io, unsigned* scratch) {
+  const int t = threadIdx.x;
+  const unsigned c0 = hist[2 * t], c1 = hist[2 * t + 1];
+  unsigned v = c0 + c1;
+  // inclusive scan over the 1024 threads
+  unsigned incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += n;
+  }
+  if ((t & 31) == 31) scratch[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    unsigned w = scratch[t];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, w, o);
+      if (t >= o) w += n;
+    }
+    scratch[32 + t] = w;  // inclusive totals per warp
+  }
+  __syncthreads();
+  const unsigned before_warp = (t >> 5) == 0 ? 0u : scratch[32 + (t >> 5) - 1];
+  incl += before_warp;
+  const unsigned excl = incl - v;
+  const unsigned r = *r_io;
+  __syncthreads();
+  if (r >= excl && r < incl) {  // exactly one thread
+    if (r - excl < c0) {
+      scratch[64] = 2 * t;
+      scratch[65] = r - excl;
+    } else {
+      scratch[64] = 2 * t + 1;
+      scratch[65] = r - excl - c0;
+    }
+    scratch[66] = (r - excl < c0) ? c0 : c1;
+  }
+  __syncthreads();
+  *r_io = scratch[65];
+  return scratch[64];
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+dyn_threshold_kernel(const float* __restrict__ xt, const float* __restrict__ pred, const float* __restrict__ gammas,
+                     int t_idx, int ptype, float image_scale, float q, float max_value, float* __restrict__ bound,
+                     long long per) {
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned scratch[72];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float g = gammas[t_idx];
+  const float a = sqrtf(g), c = sqrtf(1.0f - g);
+  const float* xb = xt + static_cast<long long>(b) * per;
+  const float* pb = pred + static_cast<long long>(b) * per;
+  // torch.quantile: ranks = q * (n - 1) as fp32; below = floor, above = ceil, weight = ranks - below
+  const float rank = __fmul_rn(q, static_cast<float>(per - 1));
+  const float below = floorf(rank);
+  const unsigned kb = static_cast<unsigned>(below), ka = static_cast<unsigned>(ceilf(rank));
+  const float w = __fsub_rn(rank, below);
+  unsigned prefix = 0, mask = 0, r = kb;
+  const int shifts[3] = {20, 10, 0}, widths[3] = {11, 10, 10};
+  unsigned count_in_bin = 0;
+  for (int ps = 0; ps < 3; ++ps) {
+    for (int i = t; i < 2048; i += DT_THREADS) hist[i] = 0;
+    __syncthreads();
+    const unsigned bm = (1u << widths[ps]) - 1u;
+    for (long long i = t; i < per; i += DT_THREADS) {
+      const unsigned u = dt_key(ptype, xb[i], pb[i], a, c, image_scale);
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shifts[ps]) & bm], 1u);
+    }
+    __syncthreads();
+    const unsigned bin = dt_find_bin(hist, &r, scratch);
+    count_in_bin = scratch[66];
+    prefix |= bin << shifts[ps];
+    mask |= bm << shifts[ps];
+    __syncthreads();
+  }
+  const unsigned u_below = prefix;  // all 31 bits fixed: the value at rank kb; r = its index among its duplicates
+  unsigned u_above = u_below;
+  if (ka != kb && r + 1 >= count_in_bin) {  // the next order statistic is the smallest value above u_below
+    if (t == 0) scratch[67] = 0xffffffffu;
+    __syncthreads();
+    unsigned m = 0xffffffffu;
+    for (long long i = t; i < per; i += DT_THREADS) {
+      const unsigned u = dt_key(ptype, xb[i], pb[i], a, c, image_scale);
+      if (u > u_below && u < m) m = u;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((t & 31) == 0) atomicMin(&scratch[67], m);
+    __syncthreads();
+    u_above = scratch[67];
+  }
+  if (t == 0) {
+    const float vb = __uint_as_float(u_below), va = __uint_as_float(u_above);
+    // at::lerp: |w| < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)
+    const float d = __fsub_rn(va, vb);
+    const float s = (fabsf(w) < 0.5f) ? __fadd_rn(vb, __fmul_rn(w, d)) : __fsub_rn(va, __fmul_rn(d, __fsub_rn(1.0f, w)));
+    bound[b] = fminf(fmaxf(s, 1.0f), max_value);
   }
 }
 
@@ -249,7 +376,36 @@ int mdm_sampler_step(const float* x_t, const float* pred, const float* noise, co
       throw mdm::MdmFail("mdm_sampler_step: noise tensor required for a stochastic step");
     mdm::sampler_step_kernel<<<mdm::grid_for(numel), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x_t, pred, noise, gammas, t_index, s_index, prediction_type, clip, image_scale, use_ddim ? 1 : 0, ddim_eta,
-        need_noise, x0_out, x_s_out, numel);
+        need_noise, x0_out, x_s_out, numel, nullptr, 1);
+    ++mdm::g_launch_count;
+    MDM_CUDA(cudaGetLastError());
+  })
+}
+
+int mdm_dynamic_threshold(const float* x_t, const float* pred, const float* gammas, int t_index, int prediction_type,
+                          float image_scale, float ratio, float max_value, float* bound, int batch, int64_t per_sample,
+                          mdm_stream_t stream) {
+  MDM_TRY({
+    if (batch < 1 || per_sample < 2 || per_sample >= (1ll << 31)) throw mdm::MdmFail("mdm_dynamic_threshold: bad sizes");
+    mdm::dyn_threshold_kernel<<<batch, mdm::DT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_t, pred, gammas, t_index, prediction_type, image_scale, ratio, max_value, bound, per_sample);
+    ++mdm::g_launch_count;
+    MDM_CUDA(cudaGetLastError());
+  })
+}
+
+int mdm_sampler_step_dynamic(const float* x_t, const float* pred, const float* noise, const float* gammas, int t_index,
+                             int s_index, int prediction_type, const float* bound, float image_scale, int use_ddim,
+                             float ddim_eta, int need_noise, float* x0_out, float* x_s_out, int batch, int64_t per_sample,
+                             mdm_stream_t stream) {
+  MDM_TRY({
+    if (bound == nullptr) throw mdm::MdmFail("mdm_sampler_step_dynamic: bound required");
+    if (need_noise && !(use_ddim && ddim_eta <= 0.f) && noise == nullptr)
+      throw mdm::MdmFail("mdm_sampler_step_dynamic: noise tensor required for a stochastic step");
+    const long long numel = static_cast<long long>(batch) * per_sample;
+    mdm::sampler_step_kernel<<<mdm::grid_for(numel), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_t, pred, noise, gammas, t_index, s_index, prediction_type, 1, image_scale, use_ddim ? 1 : 0, ddim_eta,
+        need_noise, x0_out, x_s_out, numel, bound, per_sample);
     ++mdm::g_launch_count;
     MDM_CUDA(cudaGetLastError());
   })

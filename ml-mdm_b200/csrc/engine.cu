@@ -24,6 +24,7 @@ void* Pool::alloc(size_t bytes) {
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       // drop cached blocks of other sizes and retry once
+      ++epoch_;
       for (auto& kv : free_) {
         for (void* q : kv.second) {
           cudaFree(q);
@@ -65,6 +66,7 @@ void Pool::reset() {
   in_use_ = 0;
 }
 void Pool::trim() {
+  ++epoch_;
   for (auto& kv : size_of_) cudaFree(kv.first);
   size_of_.clear();
   free_.clear();

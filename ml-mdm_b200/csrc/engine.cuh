@@ -46,12 +46,15 @@ class Pool {
   void trim();            // cudaFree everything
   size_t reserved() const { return reserved_; }
   size_t high_water() const { return high_; }
+  // bumped whenever memory goes back to the driver: addresses recorded in CUDA graphs are dead from then on
+  unsigned long long epoch() const { return epoch_; }
 
  private:
   std::unordered_map<size_t, std::vector<void*>> free_;
   std::unordered_map<void*, size_t> size_of_;
   std::unordered_map<void*, bool> live_;
   size_t reserved_ = 0, in_use_ = 0, high_ = 0;
+  unsigned long long epoch_ = 1;
 };
 
 // fp32 NHWC activation on the residual stream (or any fp32 node that receives gradients).

@@ -24,6 +24,8 @@
 
 namespace mdm {
 
+unsigned long long g_graph_launches = 0;
+
 namespace {
 
 struct ResSpec {
@@ -114,6 +116,8 @@ struct Net {
   }
 
   ~Net() {
+    for (auto& r : graphs) free_rec(r);
+    if (cap_st != nullptr) cudaStreamDestroy(cap_st);
     for (void* p : persistent) cudaFree(p);
   }
 
@@ -1469,7 +1473,7 @@ struct Net {
   }
 
   // ---------------------------------------------------------------- entry points
-  void forward(const mdm_net_io* io_, cudaStream_t st) {
+  void forward_body(const mdm_net_io* io_, cudaStream_t st) {
     eng.st = st;
     eng.training = io_->save_for_backward != 0;
     eng.tape.clear();
@@ -1495,7 +1499,7 @@ struct Net {
     io = nullptr;
   }
 
-  void backward(const mdm_net_grad_io* gio, cudaStream_t st) {
+  void backward_body(const mdm_net_grad_io* gio, cudaStream_t st) {
     MDM_CHECK(have_tape, "mdm_net_backward needs a preceding forward with save_for_backward=1");
     eng.st = st;
     // gradient scale from the largest |dout| (fp16 operands need the seed in range)
@@ -1518,6 +1522,228 @@ struct Net {
     have_tape = false;
   }
 
+
+  // ---------------------------------------------------------------- CUDA graphs
+  // One step is ~1-2.5 k launches. With graph mode on, the second call with a given shape signature is captured
+  // (forward and backward separately, on an internal stream -- torch's default stream is the legacy stream, which
+  // cannot capture) and later calls replay it: inputs are staged into per-signature static buffers, the graph is
+  // launched on the caller's stream, outputs are copied out. The first call of a signature runs eagerly and sizes the
+  // pool; pool addresses, TMA descriptors and gradient pointers are baked into the graph, so anything that moves them
+  // (rebinding parameters, the pool returning memory to the driver) drops the recorded graphs.
+  struct GraphRec {
+    int training = 0, batch = 0, tokens = 0, has_mask = 0, has_micro = 0;
+    int lb[MDM_MAX_LEVELS] = {0, 0, 0, 0}, res[MDM_MAX_LEVELS] = {0, 0, 0, 0};
+    uint64_t bind_epoch = 0, pool_epoch = 0;
+    float* x_t[MDM_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+    float* out[MDM_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+    float* dout[MDM_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+    size_t x_bytes[MDM_MAX_LEVELS] = {0, 0, 0, 0};
+    long long* times = nullptr;
+    float *lm = nullptr, *mask = nullptr, *micro = nullptr;
+    size_t lm_bytes = 0, mask_bytes = 0;
+    cudaGraphExec_t fwd = nullptr, bwd = nullptr;
+    unsigned long long fwd_kernels = 0, bwd_kernels = 0;
+    int dout_mask = 0;
+    int seen = 0;
+    uint64_t last_use = 0;
+  };
+  std::vector<GraphRec> graphs;
+  bool graph_mode = false;
+  int active_graph = -1;  // record whose forward ran last (its backward replays/captures), -1: eager
+  uint64_t bind_epoch = 1, use_clock = 0;
+  cudaStream_t cap_st = nullptr;
+  int rebinds_while_graphed = 0;
+
+  void drop_graph(GraphRec& r) {
+    if (r.fwd != nullptr) cudaGraphExecDestroy(r.fwd);
+    if (r.bwd != nullptr) cudaGraphExecDestroy(r.bwd);
+    r.fwd = r.bwd = nullptr;
+  }
+  void free_rec(GraphRec& r) {
+    drop_graph(r);
+    for (int l = 0; l < MDM_MAX_LEVELS; ++l) {
+      cudaFree(r.x_t[l]);
+      cudaFree(r.out[l]);
+      cudaFree(r.dout[l]);
+    }
+    cudaFree(r.times);
+    cudaFree(r.lm);
+    cudaFree(r.mask);
+    cudaFree(r.micro);
+  }
+  bool same_key(const GraphRec& r, const mdm_net_io* q) const {
+    if (r.training != (q->save_for_backward != 0) || r.batch != q->batch || r.tokens != q->tokens ||
+        r.has_mask != (q->lm_mask != nullptr) || r.has_micro != (q->micro_scale != nullptr))
+      return false;
+    for (int l = 0; l < cfg.num_levels; ++l)
+      if (r.res[l] != q->res[l] || r.lb[l] != (q->level_batch[l] > 0 ? q->level_batch[l] : q->batch)) return false;
+    return true;
+  }
+  int find_rec(const mdm_net_io* q) {
+    for (size_t i = 0; i < graphs.size(); ++i)
+      if (same_key(graphs[i], q)) return static_cast<int>(i);
+    if (graphs.size() >= 6) {  // bounded cache: evict the least recently used signature
+      size_t v = 0;
+      for (size_t i = 1; i < graphs.size(); ++i)
+        if (graphs[i].last_use < graphs[v].last_use) v = i;
+      free_rec(graphs[v]);
+      graphs.erase(graphs.begin() + v);
+    }
+    GraphRec r;
+    r.training = q->save_for_backward != 0;
+    r.batch = q->batch;
+    r.tokens = q->tokens;
+    r.has_mask = q->lm_mask != nullptr;
+    r.has_micro = q->micro_scale != nullptr;
+    for (int l = 0; l < cfg.num_levels; ++l) {
+      r.res[l] = q->res[l];
+      r.lb[l] = q->level_batch[l] > 0 ? q->level_batch[l] : q->batch;
+      r.x_bytes[l] = sizeof(float) * static_cast<size_t>(r.lb[l]) * cfg.in_channels * r.res[l] * r.res[l];
+      MDM_CUDA(cudaMalloc(&r.x_t[l], r.x_bytes[l]));
+      MDM_CUDA(cudaMalloc(&r.out[l], r.x_bytes[l] / cfg.in_channels * cfg.out_channels));
+      if (r.training) MDM_CUDA(cudaMalloc(&r.dout[l], r.x_bytes[l] / cfg.in_channels * cfg.out_channels));
+    }
+    MDM_CUDA(cudaMalloc(&r.times, sizeof(long long) * r.batch));
+    if (q->lm != nullptr) {
+      r.lm_bytes = sizeof(float) * static_cast<size_t>(r.batch) * r.tokens * cfg.lm_dim;
+      MDM_CUDA(cudaMalloc(&r.lm, r.lm_bytes));
+    }
+    if (r.has_mask) {
+      r.mask_bytes = sizeof(float) * static_cast<size_t>(r.batch) * r.tokens;
+      MDM_CUDA(cudaMalloc(&r.mask, r.mask_bytes));
+    }
+    if (r.has_micro) MDM_CUDA(cudaMalloc(&r.micro, sizeof(float) * r.batch));
+    graphs.push_back(r);
+    return static_cast<int>(graphs.size()) - 1;
+  }
+  cudaGraphExec_t end_capture() {
+    cudaGraph_t g = nullptr;
+    MDM_CUDA(cudaStreamEndCapture(cap_st, &g));
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) throw MdmFail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    return ex;
+  }
+  void abort_capture() {
+    cudaStreamCaptureStatus stt = cudaStreamCaptureStatusNone;
+    if (cap_st != nullptr && cudaStreamIsCapturing(cap_st, &stt) == cudaSuccess && stt != cudaStreamCaptureStatusNone) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(cap_st, &g);
+      if (g != nullptr) cudaGraphDestroy(g);
+    }
+    (void)cudaGetLastError();
+  }
+
+  void forward(const mdm_net_io* io_, cudaStream_t st) {
+    active_graph = -1;
+    if (!graph_mode || g_profile) {
+      forward_body(io_, st);
+      return;
+    }
+    const int idx = find_rec(io_);
+    GraphRec& r = graphs[idx];
+    r.last_use = ++use_clock;
+    if (r.seen == 0) {  // first call of this signature: eager, sizes the pool
+      r.seen = 1;
+      forward_body(io_, st);
+      return;
+    }
+    // stage the inputs at the addresses the graph reads
+    for (int l = 0; l < cfg.num_levels; ++l)
+      MDM_CUDA(cudaMemcpyAsync(r.x_t[l], io_->x_t[l], r.x_bytes[l], cudaMemcpyDeviceToDevice, st));
+    MDM_CUDA(cudaMemcpyAsync(r.times, io_->times, sizeof(long long) * r.batch, cudaMemcpyDeviceToDevice, st));
+    if (r.lm != nullptr) MDM_CUDA(cudaMemcpyAsync(r.lm, io_->lm, r.lm_bytes, cudaMemcpyDeviceToDevice, st));
+    if (r.has_mask) MDM_CUDA(cudaMemcpyAsync(r.mask, io_->lm_mask, r.mask_bytes, cudaMemcpyDeviceToDevice, st));
+    if (r.has_micro)
+      MDM_CUDA(cudaMemcpyAsync(r.micro, io_->micro_scale, sizeof(float) * r.batch, cudaMemcpyDeviceToDevice, st));
+    eng.st = st;
+    prepare_weights();  // outside the graph: only runs when the fp32 masters changed
+    const bool valid = r.fwd != nullptr && r.bind_epoch == bind_epoch && r.pool_epoch == eng.pool.epoch() &&
+                       (!r.training || r.bwd != nullptr);
+    if (!valid) {
+      drop_graph(r);
+      if (cap_st == nullptr) MDM_CUDA(cudaStreamCreateWithFlags(&cap_st, cudaStreamNonBlocking));
+      mdm_net_io sio = *io_;
+      for (int l = 0; l < cfg.num_levels; ++l) {
+        sio.x_t[l] = r.x_t[l];
+        sio.out[l] = r.out[l];
+      }
+      sio.times = reinterpret_cast<const int64_t*>(r.times);
+      sio.lm = r.lm;
+      sio.lm_mask = r.has_mask ? r.mask : nullptr;
+      sio.micro_scale = r.has_micro ? r.micro : nullptr;
+      const unsigned long long k0 = g_launch_count;
+      MDM_CUDA(cudaStreamBeginCapture(cap_st, cudaStreamCaptureModeRelaxed));
+      try {
+        forward_body(&sio, cap_st);
+        r.fwd = end_capture();
+      } catch (...) {
+        abort_capture();
+        eng.st = st;
+        throw;
+      }
+      r.fwd_kernels = g_launch_count - k0;
+      g_launch_count = k0;
+      r.bind_epoch = bind_epoch;
+      r.pool_epoch = eng.pool.epoch();
+      eng.st = st;
+    }
+    MDM_CUDA(cudaGraphLaunch(r.fwd, st));
+    g_launch_count += r.fwd_kernels;
+    ++g_graph_launches;
+    for (int l = 0; l < cfg.num_levels; ++l)
+      MDM_CUDA(cudaMemcpyAsync(io_->out[l], r.out[l], r.x_bytes[l] / cfg.in_channels * cfg.out_channels,
+                               cudaMemcpyDeviceToDevice, st));
+    active_graph = idx;
+  }
+
+  void backward(const mdm_net_grad_io* gio, cudaStream_t st) {
+    if (active_graph < 0) {
+      backward_body(gio, st);
+      return;
+    }
+    GraphRec& r = graphs[active_graph];
+    active_graph = -1;
+    MDM_CHECK(r.training, "mdm_net_backward needs a preceding forward with save_for_backward=1");
+    int mask = 0;
+    for (int l = 0; l < cfg.num_levels; ++l) {
+      if (gio->dout[l] == nullptr) continue;
+      mask |= 1 << l;
+      MDM_CUDA(cudaMemcpyAsync(r.dout[l], gio->dout[l], r.x_bytes[l] / cfg.in_channels * cfg.out_channels,
+                               cudaMemcpyDeviceToDevice, st));
+    }
+    if (r.bwd == nullptr) {
+      MDM_CHECK(have_tape, "graph mode: no recorded tape for this backward");
+      mdm_net_grad_io sg{};
+      for (int l = 0; l < cfg.num_levels; ++l) sg.dout[l] = (mask >> l) & 1 ? r.dout[l] : nullptr;
+      const unsigned long long k0 = g_launch_count;
+      MDM_CUDA(cudaStreamBeginCapture(cap_st, cudaStreamCaptureModeRelaxed));
+      try {
+        backward_body(&sg, cap_st);
+        r.bwd = end_capture();
+      } catch (...) {
+        abort_capture();
+        eng.st = st;
+        throw;
+      }
+      r.bwd_kernels = g_launch_count - k0;
+      g_launch_count = k0;
+      r.dout_mask = mask;
+      eng.st = st;
+      if (r.pool_epoch != eng.pool.epoch()) {  // the pool grew by freeing cached blocks: addresses in the forward graph died
+        drop_graph(r);
+        throw MdmFail("graph mode: device memory pool was trimmed during capture; retry the step");
+      }
+    } else {
+      MDM_CHECK(mask == r.dout_mask, "graph mode: the set of output gradients changed between steps");
+      MDM_CHECK(r.bind_epoch == bind_epoch, "graph mode: parameters or gradients were rebound between forward and backward");
+    }
+    MDM_CUDA(cudaGraphLaunch(r.bwd, st));
+    g_launch_count += r.bwd_kernels;
+    ++g_graph_launches;
+  }
+
   void replay_tape() {
     const int n = static_cast<int>(eng.tape.size());
     uintptr_t arena_lo = UINTPTR_MAX, arena_hi = 0;
@@ -1527,7 +1753,8 @@ struct Net {
       arena_lo = std::min(arena_lo, a);
       arena_hi = std::max(arena_hi, a + static_cast<uintptr_t>(p.numel) * sizeof(float));
     }
-    const bool notify = ready_fn != nullptr && static_cast<int>(learned.size()) == n && n > 0 && arena_hi > arena_lo;
+    const bool notify = ready_fn != nullptr && static_cast<int>(learned.size()) == n && n > 0 && arena_hi > arena_lo &&
+                        eng.st != cap_st;  // a captured backward is replayed without host code: nothing to notify
     std::vector<uintptr_t> hi_prefix;  // highest gradient end address touched by closures 0..i
     if (notify) {
       hi_prefix.assign(n, arena_lo);
@@ -1637,6 +1864,7 @@ int mdm_net_bind_param(mdm_net* net, const char* name, void* weight, void* grad)
     auto it = net->net.pindex.find(name);
     if (it == net->net.pindex.end()) throw mdm::MdmFail(std::string("unknown parameter ") + name);
     mdm::Param& p = net->net.plist[it->second];
+    if (p.w != static_cast<float*>(weight) || p.g != static_cast<float*>(grad)) ++net->net.bind_epoch;
     p.w = static_cast<float*>(weight);
     p.g = static_cast<float*>(grad);
     net->net.weights_dirty = true;
@@ -1660,6 +1888,18 @@ int mdm_net_set_grad_ready(mdm_net* net, mdm_grad_ready_fn fn, void* user, uint6
   net->net.ready_min_bytes = static_cast<size_t>(min_bytes);
   return 0;
 }
+
+int mdm_net_set_graph_mode(mdm_net* net, int enable) {
+  if (net == nullptr) return -1;
+  net->net.graph_mode = enable != 0;
+  if (!enable) {
+    for (auto& r : net->net.graphs) net->net.drop_graph(r);
+    net->net.active_graph = -1;
+  }
+  return 0;
+}
+
+unsigned long long mdm_graph_launch_count(void) { return mdm::g_graph_launches; }
 
 int mdm_net_weights_changed(mdm_net* net) {
   net->net.weights_dirty = true;

@@ -81,6 +81,7 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.mdm_last_error.restype = C.c_char_p
         l.mdm_launch_count.restype = C.c_ulonglong
+        l.mdm_graph_launch_count.restype = C.c_ulonglong
         _lib = l
     return _lib
 
@@ -97,6 +98,10 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib().mdm_launch_count())
+
+
+def graph_launch_count():
+    return int(lib().mdm_graph_launch_count())
 
 
 def tmap(ptr, dims, strides, box):

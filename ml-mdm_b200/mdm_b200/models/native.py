@@ -1,6 +1,7 @@
 """Bridge between the parameter-container modules and the native engine (mdm_net_* in
 include/mdm_b200.h).  torch is used for device memory, streams and autograd bookkeeping only."""
 import ctypes as C
+import os
 
 import torch
 
@@ -181,6 +182,15 @@ class NativeNet:
         self.offsets = None
         self._ready_cb = None
         self._keep = None
+        # CUDA-graph replay of forward / backward (mdm_net_set_graph_mode): on unless MDM_NO_GRAPH is set; switched
+        # off for this net by gradient accumulation (a fresh arena per backward would re-record every step) and while
+        # a gradient-ready callback is installed (replayed backwards run no host code)
+        self.graphs = os.environ.get("MDM_NO_GRAPH") is None
+        self.lib.mdm_net_set_graph_mode(self.handle, int(self.graphs))
+
+    def set_graph_mode(self, on):
+        self.graphs = bool(on)
+        _lib.check(self.lib.mdm_net_set_graph_mode(self.handle, int(self.graphs)), "mdm_net_set_graph_mode")
 
     def __del__(self):
         try:
@@ -266,6 +276,10 @@ class NativeNet:
 
     def _forward(self, xs, times, lm, mask, micro, save):
         self._sync_weights()
+        if save and self.graphs and self.grad_arena is not None:
+            lo, hi = self.grad_arena.data_ptr(), self.grad_arena.data_ptr() + self.grad_arena.numel() * 4
+            if any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params):
+                self.set_graph_mode(False)  # gradient accumulation: this backward needs a fresh arena (see _backward)
         io = NetIO()
         B = xs[-1].shape[0]  # the innermost level always runs the whole batch (nested_unet.py:180,200-204)
         io.batch = B
@@ -371,7 +385,10 @@ class NativeNet:
         if fn is None:
             self._ready_cb = None
             _lib.check(self.lib.mdm_net_set_grad_ready(self.handle, None, None, C.c_uint64(0)), "set_grad_ready")
+            if os.environ.get("MDM_NO_GRAPH") is None:
+                self.set_graph_mode(True)
             return
+        self.set_graph_mode(False)
         cb = _lib.GRAD_READY_FN(lambda user, lo, hi: fn(int(lo or 0), int(hi or 0)))
         self._ready_cb = cb  # keep the trampoline alive as long as the engine may call it
         _lib.check(self.lib.mdm_net_set_grad_ready(self.handle, cb, None, C.c_uint64(int(min_bytes))), "set_grad_ready")

@@ -145,14 +145,32 @@ class Sampler(nn.Module):
         return x_t
 
     # ---- reverse process
+    _DYNAMIC = {"DYNAMIC": (0.995, 100.0), "DYNAMIC_IF": (0.95, 1.5)}  # clip_sample, samplers.py:500-508
+
+    def _threshold_name(self):
+        tf = self._config.threshold_function  # the CLIs overwrite this with an enum or a plain name
+        return getattr(tf, "name", tf if isinstance(tf, str) else {0: "NONE", 1: "CLIP", 2: "DYNAMIC", 3: "DYNAMIC_IF"}.get(tf))
+
     def _clip_flag(self):
-        tf = getattr(self._config.threshold_function, "name", self._config.threshold_function)
+        tf = self._threshold_name()
         if tf == "CLIP":
             return 1
         if tf == "NONE":
             return 0
-        raise NotImplementedError("dynamic thresholding (torch.quantile per image, samplers.py:461-508) is not built "
-                                  "yet; set sampler._config.threshold_function to CLIP")
+        if tf in self._DYNAMIC:
+            return 2
+        raise ValueError(f"unknown threshold_function {self._config.threshold_function!r}")
+
+    def _dynamic_bound(self, x_t, pred, tab, t_idx, ptype, image_scale):
+        """Per-sample clip bound of dynamic thresholding (mdm_dynamic_threshold): clamp(quantile(|x0 s|, r), 1, max)."""
+        ratio, vmax = self._DYNAMIC[self._threshold_name()]
+        B = x_t.shape[0]
+        bound = torch.empty(B, device=x_t.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mdm_dynamic_threshold(_ptr(x_t), _ptr(pred), _ptr(tab), int(t_idx), int(ptype),
+                                                    C.c_float(image_scale), C.c_float(ratio), C.c_float(vmax),
+                                                    _ptr(bound), B, C.c_int64(x_t.numel() // B), _stream()),
+                   "mdm_dynamic_threshold")
+        return bound
 
     def _step_level(self, x_t, pred, t_idx, s_idx, scale, need_noise, ddim_eta, image_scale):
         x_t, pred = _f32c(x_t), _f32c(pred)
@@ -164,8 +182,18 @@ class Sampler(nn.Module):
         stochastic = bool(need_noise) and not (use_ddim and eta <= 0)
         noise = torch.randn_like(x_t) if stochastic else None
         ptype = self._config.prediction_type.value
+        clip = self._clip_flag()
+        if clip == 2:  # dynamic thresholding: exact per-sample quantile, then the same fused step kernel
+            B = x_t.shape[0]
+            bound = self._dynamic_bound(x_t, pred, tab, t_idx, ptype, image_scale)
+            _lib.check(_lib.lib().mdm_sampler_step_dynamic(_ptr(x_t), _ptr(pred), _ptr(noise), _ptr(tab), int(t_idx),
+                                                           int(s_idx), int(ptype), _ptr(bound), C.c_float(image_scale),
+                                                           int(use_ddim), C.c_float(eta), int(stochastic), _ptr(x0),
+                                                           _ptr(x_s), B, C.c_int64(x_t.numel() // B), _stream()),
+                       "mdm_sampler_step_dynamic")
+            return x0, x_s
         _lib.check(_lib.lib().mdm_sampler_step(_ptr(x_t), _ptr(pred), _ptr(noise), _ptr(tab), int(t_idx), int(s_idx),
-                                               int(ptype), self._clip_flag(), C.c_float(image_scale), int(use_ddim),
+                                               int(ptype), clip, C.c_float(image_scale), int(use_ddim),
                                                C.c_float(eta), int(stochastic), _ptr(x0), _ptr(x_s),
                                                C.c_int64(x_t.numel()), _stream()), "mdm_sampler_step")
         return x0, x_s
@@ -205,7 +233,26 @@ class Sampler(nn.Module):
         return out
 
     def clip_sample(self, pred_x0, image_scale=1):
-        return self._scale_clip(pred_x0, 1.0, True) if self._clip_flag() else pred_x0
+        """samplers.py:500-508 on an x0 tensor (the sampling loop itself uses the fused step kernels)."""
+        clip = self._clip_flag()
+        if clip == 0:
+            return pred_x0
+        x = _f32c(pred_x0)
+        s = float(image_scale)
+        if clip == 1:
+            y = self._scale_clip(x, s, True)
+            return y if s == 1.0 else self._scale_clip(y, 1.0 / s, False)
+        # dynamic: the kernels rebuild x0 from (x_t, pred) as x_t sqrt(g) - pred sqrt(1-g); with g = 1 that is x_t itself
+        one = torch.ones(1, device=x.device, dtype=torch.float32)
+        B = x.shape[0]
+        bound = self._dynamic_bound(x, x, one, 0, PredictionType.V_PREDICTION.value, s)
+        x0 = torch.empty_like(x)
+        xs = torch.empty_like(x)
+        _lib.check(_lib.lib().mdm_sampler_step_dynamic(_ptr(x), _ptr(x), None, _ptr(one), 0, 0,
+                                                       int(PredictionType.V_PREDICTION.value), _ptr(bound), C.c_float(s),
+                                                       1, C.c_float(0.0), 0, _ptr(x0), _ptr(xs), B,
+                                                       C.c_int64(x.numel() // B), _stream()), "mdm_sampler_step_dynamic")
+        return x0
 
     @staticmethod
     def _scale_clip(x, scale, clip):

@@ -110,14 +110,36 @@ def level_loss(model_out, x_t, x, eps, g, ptype, ltype):
     return ((p - t) ** 2).mean(dim=(1, 2, 3)), p, t
 
 
+def threshold_sample(sample, ratio=0.995, max_value=100.0):
+    """Sampler._threshold_sample (samplers.py:461-498): per-image quantile of |x|, clamp to [1, max], clip and divide.
+    torch.quantile (third-party arithmetic, linear interpolation on fp32 ranks) is the anchor."""
+    b = sample.shape[0]
+    flat = sample.reshape(b, -1)
+    s = torch.quantile(flat.abs(), ratio, dim=1)
+    s = torch.clamp(s, min=1, max=max_value).unsqueeze(1)
+    return (torch.clamp(flat, -s, s) / s).reshape(sample.shape)
+
+
+def clip_sample(x0, image_scale, mode):
+    """Sampler.clip_sample (samplers.py:500-508). mode: True/'CLIP', 'DYNAMIC', 'DYNAMIC_IF', False/'NONE'."""
+    if mode is True or mode == "CLIP":
+        return (x0 * image_scale).clip(-1, 1) / image_scale
+    if mode == "DYNAMIC":
+        return threshold_sample(x0 * image_scale, 0.995, 100.0) / image_scale
+    if mode == "DYNAMIC_IF":
+        return threshold_sample(x0 * image_scale, 0.95, 1.5) / image_scale
+    return x0
+
+
 def reverse_step(x_t, pred, g, g_last, ptype, clip, image_scale, ddim_eta, need_noise, noise=None):
-    """get_prediction_xt_last with scalar g, g_last (0-dim tensors). Returns (x0, x_s)."""
+    """get_prediction_xt_last with scalar g, g_last (0-dim tensors). Returns (x0, x_s).
+    clip: bool or the ThresholdType name."""
     alpha = g / g_last
     beta = 1 - alpha
     beta_tilde = beta * (1 - g_last) / (1 - g)
     x0 = x0_from_pred(x_t, pred, g.expand(x_t.shape[0]), ptype)
     if clip:
-        x0 = (x0 * image_scale).clip(-1, 1) / image_scale
+        x0 = clip_sample(x0, image_scale, clip)
     if ddim_eta is None:
         x_s = x0 * beta * g_last.sqrt() / (1 - g) + x_t * alpha.sqrt() * (1 - g_last) / (1 - g)
     else:

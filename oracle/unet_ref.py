@@ -179,7 +179,7 @@ def time_embedding(P, plan, values, l1, l2):
     """UNet.create_temporal_embedding (unet.py:834-845) with the t_emb buffer of :600-603."""
     half = plan.temporal_dim // 8
     dt = P[l1 + ".weight"].dtype
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / half)).to(dt)
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / half)).to(dt).to(values.device)
     e = values.view(-1, 1).to(dt) * freq.unsqueeze(0)
     e = torch.cat([torch.sin(e), torch.cos(e)], dim=1)
     e = F.linear(e, P[l1 + ".weight"], P[l1 + ".bias"])

@@ -183,3 +183,60 @@ def test_get_loss_mixed_ratio_batches():
         if not e <= 3e-2:
             bad[k] = e
     assert not bad, bad
+
+
+@pytest.mark.parametrize("mode,ratio,vmax", [("DYNAMIC", 0.995, 100.0), ("DYNAMIC_IF", 0.95, 1.5)])
+@pytest.mark.parametrize("res", [16, 64, 256])
+def test_dynamic_threshold_bound_is_torch_quantile_exactly(mode, ratio, vmax, res):
+    """mdm_dynamic_threshold: exact order statistics by radix select + torch.quantile's fp32 rank / lerp arithmetic
+    => the per-sample bound equals clamp(torch.quantile(|x0 s|, r), 1, max) bit for bit (samplers.py:461-498),
+    including duplicated values (quantised inputs), saturated and tiny images."""
+    import ctypes as C
+
+    from mdm_b200 import _lib
+    from mdm_b200.samplers import _ptr, _stream
+
+    g = torch.Generator().manual_seed(res)
+    B = 5
+    amp = torch.tensor([0.3, 1.0, 2.5, 40.0, 400.0]).view(B, 1, 1, 1)
+    x0 = torch.randn(B, 3, res, res, generator=g) * amp
+    x0[1] = (x0[1] * 8).round() / 8           # many exact duplicates around the quantile
+    x0 = x0.cuda()
+    one = torch.ones(1, device="cuda")
+    bound = torch.empty(B, device="cuda")
+    for scale in (1.0, 4.0):
+        _lib.check(_lib.lib().mdm_dynamic_threshold(_ptr(x0), _ptr(x0), _ptr(one), 0, 5, C.c_float(scale), C.c_float(ratio),
+                                                    C.c_float(vmax), _ptr(bound), B, C.c_int64(x0.numel() // B), _stream()),
+                   "mdm_dynamic_threshold")
+        ref = torch.clamp(torch.quantile((x0 * scale).reshape(B, -1).abs(), ratio, dim=1), min=1, max=vmax)
+        assert torch.equal(bound, ref), (bound.tolist(), ref.tolist())
+
+
+@pytest.mark.parametrize("mode", ["DYNAMIC", "DYNAMIC_IF"])
+def test_dynamic_threshold_reverse_step_and_sampling(mode):
+    """Reverse step with threshold_function = DYNAMIC / DYNAMIC_IF (the web demo's default, generate_sample.py) vs the
+    oracle (pinned bit-exactly to the reference's clip_sample), then a short sampling run through the entry point."""
+    pipe, oracle, sd, gold, x, lm, mask, nested = pipeline("nested")
+    pipe.eval()
+    smp, m = pipe.sampler, pipe.get_model()
+    smp._config.threshold_function = mode  # the CLIs assign the enum; plain names are accepted too
+    xc = [(xi * 3).cuda() for xi in x]      # large x_t: the quantile bound is active (> 1)
+    lmc, mc_ = lm.cuda(), mask.cuda()
+    with torch.no_grad():
+        x0, xs, _ = smp.get_xt_minus_1(m, 500, [a.clone() for a in xc], lmc, mc_, {}, time_step_last=480, ddim_eta=0.0,
+                                       return_details=True)
+        times = torch.full((2,), 499, dtype=torch.long, device="cuda")
+        preds = m(xc, times, lmc, mc_, {})
+    gam = dref.gammas_f32("DEEPFLOYD", 1000)
+    for xi, p, s, a, b in zip(xc, preds, [4, 1], x0, xs):
+        tab = dref.shift_table(gam, s, 1)
+        r0, rs = dref.reverse_step(xi.cpu(), p.cpu(), tab[500], tab[480], dref.V_PREDICTION, mode, 1.0, 0.0, True)
+        assert float(r0.abs().max()) <= 1.0 + 1e-6
+        assert nc.rel(a.cpu(), r0) <= 2e-6 and nc.rel(b.cpu(), rs) <= 2e-6
+    # clip_sample on a bare tensor (reference surface)
+    t = (torch.randn(2, 3, 16, 16) * 2).cuda()
+    assert nc.rel(smp.clip_sample(t, 2.0).cpu(), dref.clip_sample(t.cpu(), 2.0, mode)) <= 1e-6
+    torch.manual_seed(0)
+    out = pipe.sample(2, {"lm_outputs": lmc, "lm_mask": mc_}, 32, torch.device("cuda"), num_inference_steps=3,
+                      ddim_eta=0.0, resample_steps=True)
+    assert out.shape == (2, 3, 32, 32) and bool(torch.isfinite(out).all()) and float(out.abs().max()) <= 1.0

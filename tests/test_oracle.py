@@ -272,3 +272,17 @@ def test_oracle_mixed_ratio_loss_matches_live_reference():
     oloss.mean().backward()
     for k, p in model.named_parameters():
         close(P[k].grad, p.grad, 2e-4)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("mode", ["DYNAMIC", "DYNAMIC_IF", "CLIP", "NONE"])
+def test_oracle_clip_sample_matches_live_reference(mode):
+    """Sampler.clip_sample incl. dynamic thresholding (samplers.py:461-508): bit-identical restatement."""
+    ref = rh.load()
+    cfg = ref.samplers.SamplerConfig()
+    smp = ref.samplers.Sampler(cfg)
+    cfg.threshold_function = getattr(ref.samplers.ThresholdType, mode)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 3, 32, 32, generator=g) * torch.tensor([0.4, 1.3, 9.0]).view(3, 1, 1, 1)
+    for scale in (1.0, 4.0):
+        assert torch.equal(smp.clip_sample(x, scale), dref.clip_sample(x, scale, mode if mode != "NONE" else False))
