@@ -89,6 +89,31 @@ __device__ __forceinline__ void st_half4(__half* p, float a, float b, float c, f
   *reinterpret_cast<uint2*>(p) = v;
 }
 
+
+// Sum per-thread float4 accumulators over the pixel sub-slots that share a channel lane (lane_map: when C/4 <= TPB a
+// CTA walks TPB / lanes pixels at once), so that ONE thread per channel lane issues the global atomics. Without it a
+// 32-channel tensor has 32 sub-slots x every CTA hammering the same 32 addresses (measured on the 1024-px level of
+// cc12m_1024x1024: gn_bwd_reduce 729 us per launch, almost all of it atomic serialisation).
+// Every thread of the block must call this (it synchronises); afterwards the sums live in the threads with sub == 0.
+template <int K>
+__device__ __forceinline__ void reduce_over_subs(float4 (&v)[K], const LaneMap& m, float4* red) {
+  if (m.ppi <= 1) return;  // block-uniform
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    red[threadIdx.x] = m.active ? v[k] : make_float4(0, 0, 0, 0);
+    __syncthreads();
+    if (m.active && m.sub == 0) {
+      float4 s = red[m.t_lane];
+      for (int i = 1; i < m.ppi; ++i) {
+        const float4 o = red[m.t_lane + i * m.lanes];
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+      v[k] = s;
+    }
+    __syncthreads();
+  }
+}
+
 inline int pixel_chunks(int N, int HW, int ppi_hint, int per_sm = 8) {
   long long want = cdiv(per_sm * 148, N);
   long long maxc = cdiv(HW, ppi_hint > 0 ? ppi_hint : 1);
@@ -296,9 +321,9 @@ gn_bwd_reduce_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const f
   const int per = static_cast<int>(cdiv(HW, gridDim.x));
   const int p_begin = blockIdx.x * per;
   const int p_end = min(HW, p_begin + per);
-  if (!m.active) return;
+  __shared__ float4 red[TPB];
   GnCoef<NL> k;
-  gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  if (m.active) gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
   float4 A[NL], Bq[NL];
 #pragma unroll
   for (int j = 0; j < NL; ++j) {
@@ -306,7 +331,7 @@ gn_bwd_reduce_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const f
     Bq[j] = make_float4(0, 0, 0, 0);
   }
   constexpr int U = PixUnroll<NL>::U;
-  for (int p0 = p_begin + m.sub; p0 < p_end; p0 += U * m.ppi) {
+  for (int p0 = p_begin + m.sub; m.active && p0 < p_end; p0 += U * m.ppi) {
     float4 vv[U][NL], dd[U][NL];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -345,6 +370,9 @@ gn_bwd_reduce_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const f
       }
     }
   }
+  reduce_over_subs(A, m, red);
+  reduce_over_subs(Bq, m, red);
+  if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
 #pragma unroll
   for (int j = 0; j < NL; ++j) {
     const int l = m.t_lane + j * m.stride;
@@ -410,9 +438,9 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
   const int per = static_cast<int>(cdiv(HW, gridDim.x));
   const int p_begin = blockIdx.x * per;
   const int p_end = min(HW, p_begin + per);
-  if (!m.active) return;
+  __shared__ float4 red[TPB];
   GnCoef<NL> k;
-  gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  if (m.active) gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
   float4 csum[NL];
 #pragma unroll
   for (int j = 0; j < NL; ++j) csum[j] = make_float4(0, 0, 0, 0);
@@ -422,7 +450,7 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
 #pragma unroll
   for (int j = 0; j < NL; ++j) {
     const int l = m.t_lane + j * m.stride;
-    if (l < m.lanes) {
+    if (m.active && l < m.lanes) {
       float a[4], b[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -435,7 +463,7 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
     }
   }
   constexpr int U = NL == 1 ? 2 : 1;  // measured: 4 pixels per trip costs this kernel a resident CTA (92 regs)
-  for (int p0 = p_begin + m.sub; p0 < p_end; p0 += U * m.ppi) {
+  for (int p0 = p_begin + m.sub; m.active && p0 < p_end; p0 += U * m.ppi) {
     float4 vv[U][NL], dd[U][NL];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -504,7 +532,9 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
     }
     }
   }
-  if (dst.h16 != nullptr && dst.colsum != nullptr) {
+  if (dst.h16 != nullptr && dst.colsum != nullptr) {  // kernel-argument condition: uniform over the block
+    reduce_over_subs(csum, m, red);
+    if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
     const float inv = dst.inv_scale != nullptr ? __ldg(dst.inv_scale) : 1.f;
 #pragma unroll
     for (int j = 0; j < NL; ++j) {
@@ -531,11 +561,11 @@ cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, lon
   const long long per = cdiv(rows, gridDim.x);
   const long long r_begin = blockIdx.x * per;
   const long long r_end = min(rows, r_begin + per);
-  if (!m.active) return;
+  __shared__ float4 red[TPB];
   float4 s = make_float4(0, 0, 0, 0);
   const int c = c0 + 4 * m.t_lane;
   constexpr int U = 4;  // rows per trip: all loads issued before the first use
-  for (long long r = r_begin + m.sub; r < r_end; r += U * m.ppi) {
+  for (long long r = r_begin + m.sub; m.active && r < r_end; r += U * m.ppi) {
     float4 v[U];
     uint2 raw[U];
 #pragma unroll
@@ -562,6 +592,12 @@ cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, lon
     }
   }
   if (colsum == nullptr) return;
+  {
+    float4 sv[1] = {s};
+    reduce_over_subs(sv, m, red);
+    s = sv[0];
+  }
+  if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
   const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
   atomicAdd(colsum + c + 0, inv * s.x);
   atomicAdd(colsum + c + 1, inv * s.y);

@@ -119,6 +119,9 @@ def run_case(name, B=1, S=8, micro=False, verbose=False):
     tm["ours"] = time.time() - t0
     rep = {"out": [(rel(a, r), rel(b, r)) for a, b, r in zip(oo, o32, o64)], "grads": {}, "seconds": tm,
            "missing": [k for k in g64 if k not in go]}
+    rep["grad_absmax"] = {k: float(go[k].abs().max()) for k in go}
+    mags = sorted(float(r.abs().max()) for r in g64.values())
+    rep["grad_typical"] = mags[len(mags) // 2]  # median over parameters of max|d loss / d parameter|
     for k, r in g64.items():
         if k in go:
             rep["grads"][k] = (rel(go[k], r), rel(g32[k], r))
@@ -126,9 +129,12 @@ def run_case(name, B=1, S=8, micro=False, verbose=False):
         print(f"== {name} B={B} S={S} micro={micro}: seconds {tm}")
         for i, (a, b) in enumerate(rep["out"]):
             print(f"   out[{i}]  ours {a:.3e}   reference-tf32 {b:.3e}")
-        ge = sorted(rep["grads"].items(), key=lambda kv: -kv[1][0])
-        ours = sorted(v[0] for v in rep["grads"].values())
-        ref = sorted(v[1] for v in rep["grads"].values())
+        defined = {k: v for k, v in rep["grads"].items() if v[1] <= 0.5}
+        print(f"   numerically undefined gradients (reference-tf32 error > 0.5, mathematically zero): "
+              f"{sorted(k for k in rep['grads'] if k not in defined)}")
+        ge = sorted(defined.items(), key=lambda kv: -kv[1][0])
+        ours = sorted(v[0] for v in defined.values())
+        ref = sorted(v[1] for v in defined.values())
         n = len(ours)
         print(f"   {n} parameter gradients: ours median {ours[n // 2]:.3e} p90 {ours[int(.9 * n)]:.3e} max {ours[-1]:.3e} | "
               f"reference-tf32 median {ref[n // 2]:.3e} p90 {ref[int(.9 * n)]:.3e} max {ref[-1]:.3e}")

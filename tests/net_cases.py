@@ -62,6 +62,20 @@ def run_case(kind, batch=2, tokens=6, dtype=torch.float64, verbose=True, res=Non
     torch.cuda.synchronize()
 
     report = {"out": [rel(o.detach().cpu().to(dtype), r.detach()) for o, r in zip(outs, o_outs)]}
+    # calibration: the same oracle in fp32 on the GPU with TF32 enabled = the arithmetic the reference trains with
+    # (clis/train_parallel.py:18-19); its error against the fp64 oracle, measured with the same metric
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        Pt = {k: v.float().cuda().requires_grad_(True) for k, v in sd.items()}
+        t_out = oracle.forward(Pt, [xi.cuda() for xi in xs] if nlev > 1 else xs[0].cuda(), t.cuda(), lm.cuda(), mask.cuda(), {})
+        t_outs = [t_out] if nlev == 1 else list(t_out)
+        sum((o * w.cuda()).sum() for o, w in zip(t_outs, ws)).backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    report["tf32_out"] = [rel(o.detach().cpu().to(dtype), r.detach()) for o, r in zip(t_outs, o_outs)]
     # intermediates
     acts = {}
     for name, ref in trace.items():
@@ -85,11 +99,17 @@ def run_case(kind, batch=2, tokens=6, dtype=torch.float64, verbose=True, res=Non
             continue
         got = p.grad.detach().cpu().to(dtype)
         grads[k] = float((got - ref).abs().max() / max(float(ref.abs().max()), floor))
+        report.setdefault("tf32_grads", {})[k] = float((Pt[k].grad.detach().cpu().to(dtype) - ref).abs().max()
+                                                       / max(float(ref.abs().max()), floor))
         if verbose and not (grads[k] <= 5e-2):
             print("   BAD", k, "got", p.grad.detach().flatten()[:6].tolist(), "ref", ref.flatten()[:6].tolist())
     report["grads"] = grads
     if verbose:
-        print(f"== {kind}: out rel err {report['out']}")
+        print(f"== {kind}: out rel err {report['out']}  (reference-tf32: {report['tf32_out']})")
+        tg = sorted(report["tf32_grads"].values())
+        og = sorted(grads.values())
+        print(f"   grads: ours median {og[len(og) // 2]:.2e} max {og[-1]:.2e} | reference-tf32 median {tg[len(tg) // 2]:.2e} "
+              f"max {tg[-1]:.2e}")
         bad_a = {k: v for k, v in acts.items() if isinstance(v, str) or v > 2e-3}
         print(f"   activations checked: {len(acts)}, above 2e-3: {bad_a}")
         worst = sorted(grads.items(), key=lambda kv: -(kv[1] if kv[1] == kv[1] else 1e9))[:12]

@@ -87,46 +87,7 @@ def test_batch_independence_full_width():
     assert nc.rel(one, full[1:2]) <= 3e-3
 
 
-@pytest.mark.parametrize("name", ["cc12m_64x64", "cc12m_256x256"])
-def test_shipped_config_forward_vs_oracle_full_width(name):
-    """The shipped architectures at full width (461 M / 477 M parameters), batch 1, S=32 tokens:
-    native forward vs the fp32 oracle on the host. Bound 5e-3: ~100 fp16-operand layers deep."""
-    import copy
-    import types
-
-    import yaml
-
-    from mdm_b200 import config as mc
-    from mdm_b200.models import NestedUNet, UNet
-    from oracle import unet_ref
-
-    cfgp = os.path.join(os.path.dirname(GOLD), "..", "ml-mdm_b200", "mdm_b200", "configs", name + ".yaml")
-    ucfg, _, nested = mc.load_yaml_configs(cfgp)
-    ocfg = copy.deepcopy(ucfg)
-    torch.manual_seed(0)
-    m = (NestedUNet if nested else UNet)(3, 3, ucfg)
-    with torch.no_grad():
-        for p in m.parameters():
-            if float(p.abs().max()) == 0:
-                p.normal_(0, 0.02)
-    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    res = [256, 64] if nested else [64]
-    g = torch.Generator().manual_seed(1)
-    xs = [torch.randn(1, 3, r, r, generator=g) for r in res]
-    t = torch.tensor([437])
-    lm = torch.randn(1, 32, 2048, generator=g)
-    mask = torch.ones(1, 32)
-    torch.set_num_threads(min(os.cpu_count() or 1, 32))
-    net = unet_ref.OracleNet(ocfg, 2048)
-    with torch.no_grad():
-        ref = net.forward(sd, xs if nested else xs[0], t, lm, mask, {})
-    refs = list(ref) if nested else [ref]
-    m = m.cuda()
-    with torch.no_grad():
-        out = m([x.cuda() for x in xs] if nested else xs[0].cuda(), t.cuda(), lm.cuda(), mask.cuda(), {})
-    outs = list(out) if nested else [out]
-    for o, r in zip(outs, refs):
-        assert nc.rel(o.cpu(), r) <= 5e-3
+# (full-width forward AND backward parity of the three shipped configs: tests/test_fullwidth_gpu.py)
 
 
 @pytest.mark.gpu

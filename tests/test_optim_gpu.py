@@ -195,7 +195,8 @@ def test_ema_engine_sees_fused_updates():
         fresh = copy.deepcopy(ema.module)               # no cached engine: packs from the current fp32 values
         e2 = fresh(xs, t, lm, mask, {})
     assert float((e1 - e0).abs().max()) > 0, "EMA forward still uses the weights packed before the updates"
-    assert torch.equal(e1, e2)
+    # not bit-identical run to run: GroupNorm partial sums are combined by fp32 atomics
+    assert float((e1 - e2).abs().max()) <= 1e-3 * float(e2.abs().max())
 
 
 def test_fused_adam_state_dict_round_trip_matches_torch_adam():
