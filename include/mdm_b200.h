@@ -153,6 +153,9 @@ typedef struct mdm_net_io {
    * level_batch[l] samples. Where an outer level is narrower than its inner one the in_adapter output is
    * zero-padded and only the leading rows of the out_adapter result are used, as in the reference. */
   int32_t level_batch[MDM_MAX_LEVELS];
+  /* 1: lm is the raw encoder output and is multiplied by lm_mask on the way in (what language_models/factory.py:101
+   * does as a separate (B,S,D) pass before the model is called); needs lm_mask and the lm_proj layer. */
+  int32_t apply_lm_mask;
 } mdm_net_io;
 
 /* CUDA-graph execution of forward / backward (off by default). With it on, the first call with a given shape
@@ -250,6 +253,13 @@ int mdm_adam_ema_sweep(const mdm_opt_chunk* chunks_dev, int32_t nchunks, const m
 /* x_t = sqrt(g) * (x / image_div) + sqrt(1-g) * eps with g = gammas[t[b] + t_offset]  (samplers.py:244-246) */
 int mdm_q_sample(const float* x, const float* eps, const int64_t* t, const float* gammas, int t_offset,
                  float image_div, float* x_t, int batch, int64_t per_sample, mdm_stream_t stream);
+/* Input side of the path (clis/train_parallel.py:193-199): the data loader hands over uint8 NHWC
+ * images and the trainer computes images = (x.float() - 127) / 128, permuted to NCHW, before get_loss noises them.
+ * One pass: x (batch, channels, H, W) fp32 = (u8 - 127) / 128 and, when x_t != NULL, x_t = q-sample of it as
+ * mdm_q_sample does. images_u8: (batch, H, W, channels). */
+int mdm_q_sample_u8(const uint8_t* images_u8, const float* eps, const int64_t* t, const float* gammas, int t_offset,
+                    float image_div, float* x, float* x_t, int batch, int channels, int height, int width,
+                    mdm_stream_t stream);
 /* loss[b] += weight * mean_chw (pred_for_training - target)^2 with g = gammas[t[b] + 1]
  * (diffusion.py:123-136,160-168; samplers.py:266-279). loss must be zero-initialised by the caller.
  * pred_out / tgt_out (optional) receive the converted prediction and the target. */

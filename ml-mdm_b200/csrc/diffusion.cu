@@ -49,6 +49,36 @@ __global__ void q_sample_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+
+// uint8 NHWC image -> normalised fp32 NCHW image x = (u - 127) / 128 (clis/train_parallel.py:193-195) and, in the same
+// pass, x_t = sqrt(g) x / div + sqrt(1-g) eps. One thread per pixel: reads its C interleaved bytes, writes C planes.
+__global__ void q_sample_u8_kernel(const uint8_t* __restrict__ u8, const float* __restrict__ eps,
+                                   const long long* __restrict__ t, const float* __restrict__ gammas, int t_off,
+                                   float image_div, float* __restrict__ x, float* __restrict__ xt, int C, long long HW,
+                                   long long total_pix) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total_pix; i += gs) {
+    const long long b = i / HW, p = i - b * HW;
+    float sg = 0.f, sn = 0.f;
+    if (xt != nullptr) {
+      const float g = gammas[t[b] + t_off];
+      sg = sqrtf(g);
+      sn = sqrtf(1.0f - g);
+    }
+    for (int c = 0; c < C; ++c) {
+      // same two fp32 roundings as the reference's (x.float() - 127.0) / 128.0 (both exact here)
+      const float v = __fdiv_rn(__fsub_rn(static_cast<float>(u8[i * C + c]), 127.0f), 128.0f);
+      const long long o = (b * C + c) * HW + p;
+      x[o] = v;
+      if (xt != nullptr) {
+        const float vi = image_div != 1.0f ? v / image_div : v;
+        xt[o] = __fadd_rn(__fmul_rn(sg, vi), __fmul_rn(sn, eps[o]));
+      }
+    }
+  }
+}
+
 // loss[b] = mean_chw (pred_loss - target)^2 * weight ; optionally writes pred_loss / target.
 // One block per (sample, chunk); partial sums by atomics into loss (zeroed by the launcher).
 __global__ void __launch_bounds__(256)
@@ -334,6 +364,21 @@ int mdm_q_sample(const float* x, const float* eps, const int64_t* t, const float
     const long long total = static_cast<long long>(batch) * per_sample;
     mdm::q_sample_kernel<<<mdm::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, eps, reinterpret_cast<const long long*>(t), gammas, t_offset, image_div, x_t, per_sample, total);
+    ++mdm::g_launch_count;
+    MDM_CUDA(cudaGetLastError());
+  })
+}
+
+int mdm_q_sample_u8(const uint8_t* images_u8, const float* eps, const int64_t* t, const float* gammas, int t_offset,
+                    float image_div, float* x, float* x_t, int batch, int channels, int height, int width,
+                    mdm_stream_t stream) {
+  MDM_TRY({
+    if (x == nullptr || images_u8 == nullptr) throw mdm::MdmFail("mdm_q_sample_u8: images_u8 and x are required");
+    if (x_t != nullptr && (eps == nullptr || t == nullptr || gammas == nullptr))
+      throw mdm::MdmFail("mdm_q_sample_u8: eps, t and gammas are required when x_t is requested");
+    const long long HW = static_cast<long long>(height) * width, total = HW * batch;
+    mdm::q_sample_u8_kernel<<<mdm::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        images_u8, eps, reinterpret_cast<const long long*>(t), gammas, t_offset, image_div, x, x_t, channels, HW, total);
     ++mdm::g_launch_count;
     MDM_CUDA(cudaGetLastError());
   })

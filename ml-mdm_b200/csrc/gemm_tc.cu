@@ -524,7 +524,9 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
   const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
   static const int budget_kb = getenv("MDM_SMEM_BUDGET_KB") ? atoi(getenv("MDM_SMEM_BUDGET_KB")) : 0;  // dev knob
-  const int budget = budget_kb > 0 ? budget_kb * 1024 : SMEM_BUDGET;
+  static const int narrow_kb = getenv("MDM_SMEM_NARROW_KB") ? atoi(getenv("MDM_SMEM_NARROW_KB")) : 0;      // dev knob
+  int budget = budget_kb > 0 ? budget_kb * 1024 : SMEM_BUDGET;
+  if (narrow_kb > 0 && p.block_n <= 64) budget = narrow_kb * 1024;  // more co-resident CTAs for narrow tiles
   int stages = (budget - 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int per = (p.num_kblocks + p.nsplit - 1) / p.nsplit;
@@ -600,7 +602,8 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   {
     const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
     const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
-    if (persistent && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
+    static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 0;  // dev knob
+    if (persistent && p.block_n >= persist_min_n && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
       return launch_gemm_persistent(tmA, tmB, tmO, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }
 

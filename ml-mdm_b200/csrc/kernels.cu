@@ -617,6 +617,20 @@ __global__ void cast_f32_to_f16_kernel(const float* __restrict__ in, __half* __r
   }
 }
 
+// out[r][:] = half(in[r][:] * rowscale[r])  (T5 features times their 0/1 token mask, language_models/factory.py:101)
+__global__ void cast_rowscale_f16_kernel(const float* __restrict__ in, const float* __restrict__ rowscale,
+                                         __half* __restrict__ out, long long rows, int D) {
+  const int per_row = D / 4;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x, total = rows * per_row;
+  for (; i < total; i += stride) {
+    const long long r = i / per_row;
+    const float m = __ldg(rowscale + r);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    st_half4(out + 4 * i, v.x * m, v.y * m, v.z * m, v.w * m);
+  }
+}
+
 __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ a,
                                const float* __restrict__ b, long long n) {
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1243,6 +1257,10 @@ void colsum_f16(const __half* in, long long rows, int C, float* colsum, const fl
 }
 void cast_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st) {
   cast_f32_to_f16_kernel<<<grid_for(cdiv(n, 4)), 256, 0, st>>>(in, out, n);
+  MDM_LAUNCHED();
+}
+void cast_rowscale_f16(const float* in, const float* rowscale, __half* out, long long rows, int D, cudaStream_t st) {
+  cast_rowscale_f16_kernel<<<grid_for(rows * (D / 4)), 256, 0, st>>>(in, rowscale, out, rows, D);
   MDM_LAUNCHED();
 }
 void add_f32(float* dst, const float* a, const float* b, long long n, cudaStream_t st) {

@@ -56,6 +56,8 @@ void cast_colsum(const float* in, __half* out16, long long rows, int C, float* c
 void colsum_f16(const __half* in, long long rows, int C, float* colsum, const float* inv_scale,
                 cudaStream_t st);
 void cast_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st);
+// out16[r][:] = half(in[r][:] * rowscale[r]); D % 4 == 0
+void cast_rowscale_f16(const float* in, const float* rowscale, __half* out16, long long rows, int D, cudaStream_t st);
 void add_f32(float* dst, const float* a, const float* b, long long n, cudaStream_t st);  // dst = a + b
 void axpy_f32(float* dst, const float* a, float alpha, long long n, int acc, cudaStream_t st);
 

@@ -1181,13 +1181,19 @@ struct Net {
     if (cfg.has_lm_proj) {
       Param &w = P(L.pre + "lm_proj.weight"), &b = P(L.pre + "lm_proj.bias");
       cs.lm16 = E.alloc<__half>(crow * cfg.lm_dim);
-      cast_f32_to_f16(io->lm, cs.lm16, crow * cfg.lm_dim, E.st);
+      if (io->apply_lm_mask) {
+        MDM_CHECK(io->lm_mask != nullptr && cfg.lm_dim % 4 == 0, "apply_lm_mask needs lm_mask");
+        cast_rowscale_f16(io->lm, io->lm_mask, cs.lm16, crow, cfg.lm_dim, E.st);
+      } else {
+        cast_f32_to_f16(io->lm, cs.lm16, crow * cfg.lm_dim, E.st);
+      }
       cs.cond32 = E.alloc<float>(crow * cfg.cond_dim);
       Epi e;
       e.bias = b.w;
       e.out_f32 = cs.cond32;
       E.gemm_nt(cs.lm16, cfg.lm_dim, w.w16, cfg.lm_dim, static_cast<int>(crow), cfg.cond_dim, cfg.lm_dim, e);
     } else {
+      MDM_CHECK(!io->apply_lm_mask, "apply_lm_mask is only built for models with an lm_proj layer");
       cs.cond32 = const_cast<float*>(io->lm);
     }
     {  // LayerNorm(cond) without its affine part, once per forward (31 blocks share it; unet.py:263,304)
@@ -1531,7 +1537,7 @@ struct Net {
   // pool; pool addresses, TMA descriptors and gradient pointers are baked into the graph, so anything that moves them
   // (rebinding parameters, the pool returning memory to the driver) drops the recorded graphs.
   struct GraphRec {
-    int training = 0, batch = 0, tokens = 0, has_mask = 0, has_micro = 0;
+    int training = 0, batch = 0, tokens = 0, has_mask = 0, has_micro = 0, apply_lm_mask = 0;
     int lb[MDM_MAX_LEVELS] = {0, 0, 0, 0}, res[MDM_MAX_LEVELS] = {0, 0, 0, 0};
     uint64_t bind_epoch = 0, pool_epoch = 0;
     float* x_t[MDM_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
@@ -1573,6 +1579,7 @@ struct Net {
   }
   bool same_key(const GraphRec& r, const mdm_net_io* q) const {
     if (r.training != (q->save_for_backward != 0) || r.batch != q->batch || r.tokens != q->tokens ||
+        r.apply_lm_mask != (q->apply_lm_mask != 0) ||
         r.has_mask != (q->lm_mask != nullptr) || r.has_micro != (q->micro_scale != nullptr))
       return false;
     for (int l = 0; l < cfg.num_levels; ++l)
@@ -1595,6 +1602,7 @@ struct Net {
     r.tokens = q->tokens;
     r.has_mask = q->lm_mask != nullptr;
     r.has_micro = q->micro_scale != nullptr;
+    r.apply_lm_mask = q->apply_lm_mask != 0;
     for (int l = 0; l < cfg.num_levels; ++l) {
       r.res[l] = q->res[l];
       r.lb[l] = q->level_batch[l] > 0 ? q->level_batch[l] : q->batch;

@@ -176,15 +176,35 @@ class Diffusion(nn.Module):
         sc = self._config.sampler_config
         return int(sc.prediction_type.value), int(sc.loss_target_type.value)
 
+    def _inputs(self, sample):
+        """(images or uint8 batch, lm_outputs, lm_mask). Besides the reference's keys, the raw reader batch is accepted:
+        sample["image"] uint8 NHWC instead of "images" (the (x - 127) / 128 + permute of train_parallel.py:193-195 is
+        then fused into the q-sample kernel), and sample["lm_mask_applied"] = False when lm_outputs has not been
+        multiplied by lm_mask yet (language_models/factory.py:101; fused into the engine's input cast)."""
+        self.get_model().vision_model.fuse_lm_mask = sample.get("lm_mask_applied", True) is False
+        images = sample["images"] if "images" in sample else sample["image"]
+        return images, sample["lm_outputs"], sample["lm_mask"]
+
+    def _draw(self, images):
+        """get_eps_time for a float NCHW or a uint8 NHWC batch (same generator draws either way)."""
+        if images.dtype == torch.uint8:
+            B, H, W, Cc = images.shape
+            like = torch.empty(B, Cc, H, W, device=images.device, dtype=torch.float32)
+            return self.sampler.get_eps_time(like)
+        return self.sampler.get_eps_time(images)
+
     def get_loss(self, sample: dict):
         """diffusion.py:144-168."""
-        images, lm_outputs, lm_mask = sample["images"], sample["lm_outputs"], sample["lm_mask"]
+        images, lm_outputs, lm_mask = self._inputs(sample)
         sc = self._config.sampler_config
-        eps, time, weights = self.sampler.get_eps_time(images)
+        eps, time, weights = self._draw(images)
         if not self._config.use_vdm_loss_weights:
             weights = None
         rs = sc.rescale_signal
-        x_t = self.sampler.q_sample(images, eps, time, scale=1.0, image_div=float(rs) if rs else 1.0)
+        if images.dtype == torch.uint8:
+            images, x_t = self.sampler.q_sample_u8(images, eps, time, scale=1.0, image_div=float(rs) if rs else 1.0)
+        else:
+            x_t = self.sampler.q_sample(images, eps, time, scale=1.0, image_div=float(rs) if rs else 1.0)
         micros = self.get_micro_conditioning(sample)
         means, _ = self.model(x_t, time, lm_outputs, lm_mask, micros)
         ptype, ltype = self._types()
@@ -192,6 +212,7 @@ class Diffusion(nn.Module):
                     levels=[dict(table=self.sampler.level_table(1.0, images.device), image_div=1.0, weight=1.0,
                                  want_outputs=True)])
         loss, pred, tgt = _LossFn.apply(spec, time, means, x_t, _f32c(images), eps)
+        self.get_model().vision_model.fuse_lm_mask = False
         return loss, time, x_t, means, tgt, weights
 
     def get_noise(self, num_examples, input_channels, image_side, device):
@@ -230,24 +251,29 @@ class NestedDiffusion(Diffusion):
     def get_loss(self, sample: dict):
         """diffusion.py:315-387: image pyramid by average pooling, fresh low-resolution noise,
         per-level shifted schedule, weighted sum of per-level MSE."""
-        images, lm_outputs, lm_mask = sample["images"], sample["lm_outputs"], sample["lm_mask"]
+        images, lm_outputs, lm_mask = self._inputs(sample)
         micros = self.get_micro_conditioning(sample)
         vm = self.get_model().vision_model
         scales = vm.nest_ratio + [1]
         ratios = [scales[0] // s for s in scales]
         if any(vm.is_temporal):
             raise NotImplementedError("temporal mode")
-        eps0, time, weights = self.sampler.get_eps_time(images)
+        eps0, time, weights = self._draw(images)
         if not self._config.use_vdm_loss_weights:
             weights = None
+        xt0 = None
+        if images.dtype == torch.uint8:  # fused (x - 127) / 128, NHWC -> NCHW and the full-resolution q-sample
+            images, xt0 = self.sampler.q_sample_u8(images, eps0, time, scale=scales[0],
+                                                   image_div=self.sampler.level_image_div(scales[0]))
         imgs, epss = [_f32c(images)], [eps0]
         for iz in range(1, len(ratios)):
             rr = ratios[iz] // ratios[iz - 1]
             imgs.append(self.avg_pool(imgs[-1], rr))
         for iz in range(1, len(ratios)):
             epss.append(torch.empty_like(imgs[iz]).normal_())
-        x_t = [self.sampler.q_sample(x, e, time, scale=s, image_div=self.sampler.level_image_div(s))
-               for x, e, s in zip(imgs, epss, scales)]
+        x_t = [xt0 if (i == 0 and xt0 is not None) else
+               self.sampler.q_sample(x, e, time, scale=s, image_div=self.sampler.level_image_div(s))
+               for i, (x, e, s) in enumerate(zip(imgs, epss, scales))]
         p_t = self.model(x_t, time, lm_outputs, lm_mask, micros, self.mixed_ratio)
         if self._config.multi_res_weights is not None:
             assert self._config.use_double_loss, "only makes sense when applying more losses"
@@ -268,4 +294,5 @@ class NestedDiffusion(Diffusion):
             levels.append(lv)
             flat += [p, xt, x, e]
         loss, pred0, tgt0 = _LossFn.apply(dict(ptype=ptype, ltype=ltype, levels=levels), time, *flat)
+        vm.fuse_lm_mask = False
         return loss, time, x_t[0], pred0, tgt0, weights

@@ -56,6 +56,7 @@ class NetIO(C.Structure):
         ("out", C.c_void_p * MAX_LEVELS),
         ("save_for_backward", C.c_int32),
         ("level_batch", C.c_int32 * MAX_LEVELS),
+        ("apply_lm_mask", C.c_int32),
     ]
 
 
@@ -123,7 +124,7 @@ class _DenoiseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, native, nlev, need_grad, times, lm, mask, micro, *rest):
         xs = rest[:nlev]
-        outs = native._forward(list(xs), times, lm, mask, micro, save=need_grad)
+        outs = native._forward(list(xs), times, lm, mask, micro, save=need_grad, apply_lm_mask=native.apply_lm_mask)
         ctx.native = native
         ctx.nlev = nlev
         ctx.set_materialize_grads(False)
@@ -182,6 +183,7 @@ class NativeNet:
         self.offsets = None
         self._ready_cb = None
         self._keep = None
+        self.apply_lm_mask = False
         # CUDA-graph replay of forward / backward (mdm_net_set_graph_mode): on unless MDM_NO_GRAPH is set; switched
         # off for this net by gradient accumulation (a fresh arena per backward would re-record every step) and while
         # a gradient-ready callback is installed (replayed backwards run no host code)
@@ -265,8 +267,9 @@ class NativeNet:
             self.versions = v
 
     # ---------------------------------------------------------------- public
-    def run(self, xs, times, lm, mask, micros):
+    def run(self, xs, times, lm, mask, micros, apply_lm_mask=False):
         self._bind()
+        self.apply_lm_mask = bool(apply_lm_mask)
         micro = None
         if micros:
             micro = micros.get("scale", None)
@@ -274,7 +277,7 @@ class NativeNet:
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
         return _DenoiseFn.apply(self, len(xs), need_grad, times, lm, mask, micro, *xs, *self.params)
 
-    def _forward(self, xs, times, lm, mask, micro, save):
+    def _forward(self, xs, times, lm, mask, micro, save, apply_lm_mask=False):
         self._sync_weights()
         if save and self.graphs and self.grad_arena is not None:
             lo, hi = self.grad_arena.data_ptr(), self.grad_arena.data_ptr() + self.grad_arena.numel() * 4
@@ -322,6 +325,7 @@ class NativeNet:
             micro = f32(micro)
             io.micro_scale = micro.data_ptr()
         io.save_for_backward = int(save)
+        io.apply_lm_mask = int(bool(apply_lm_mask))
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.mdm_net_forward(self.handle, C.byref(io), C.c_void_p(st)), "mdm_net_forward")
         self._keep = keep if save else None  # inputs must outlive the tape

@@ -237,5 +237,8 @@ class UNet(nn.Module):
         """UNet.forward (unet.py:971-987). x_t: (B, C, R, R) fp32 cuda tensor."""
         single = not isinstance(x_t, (list, tuple))
         xs = [x_t] if single else list(x_t)
-        outs = self.native().run(xs, times, conditioning, cond_mask, micros)
+        # fuse_lm_mask: `conditioning` is the raw encoder output; the engine multiplies it by cond_mask on the way in
+        # (language_models/factory.py:101 does that as a separate pass before the model is called)
+        outs = self.native().run(xs, times, conditioning, cond_mask, micros,
+                                 apply_lm_mask=bool(getattr(self, "fuse_lm_mask", False)))
         return outs[0] if single else list(outs)

@@ -144,6 +144,19 @@ class Sampler(nn.Module):
                                            _ptr(x_t), B, C.c_int64(images.numel() // B), _stream()), "mdm_q_sample")
         return x_t
 
+    def q_sample_u8(self, images_u8, eps, time, scale=1.0, image_div=1.0):
+        """uint8 NHWC batch (as the data loader yields it, train_parallel.py:193-195) -> (normalised fp32 NCHW images,
+        x_t) in one pass (mdm_q_sample_u8)."""
+        assert images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.is_contiguous()
+        B, H, W, Cc = images_u8.shape
+        x = torch.empty(B, Cc, H, W, device=images_u8.device, dtype=torch.float32)
+        x_t = torch.empty_like(x)
+        tab = self.level_table(scale, images_u8.device)
+        _lib.check(_lib.lib().mdm_q_sample_u8(_ptr(images_u8), _ptr(_f32c(eps)), _ptr(time), _ptr(tab), 1,
+                                              C.c_float(image_div), _ptr(x), _ptr(x_t), B, Cc, H, W, _stream()),
+                   "mdm_q_sample_u8")
+        return x, x_t
+
     # ---- reverse process
     _DYNAMIC = {"DYNAMIC": (0.995, 100.0), "DYNAMIC_IF": (0.95, 1.5)}  # clip_sample, samplers.py:500-508
 

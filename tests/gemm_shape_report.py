@@ -39,8 +39,17 @@ def main(cfg="cc12m_64x64", B=64):
         agg[key][0] += float(r["ms"]); agg[key][1] += flops(r); agg[key][2] += 1
     T = sum(v[0] for v in agg.values()); F = sum(v[1] for v in agg.values())
     print(f"total {T:.2f} ms, {F/1e12:.1f} TFLOP issued, {F/T/1e9:.0f} TFLOP/s avg over {len(rows)} launches")
+    bucket = collections.defaultdict(lambda: [0.0, 0])
+    for r in rows:
+        n = int(r["N"])
+        b = "N<=32" if n <= 32 else ("N<=64" if n <= 64 else ("N<=128" if n <= 128 else "N>128"))
+        kind = {"0": "plain", "1": "conv", "2": "wgrad"}[r["kind"]]
+        bucket[(kind, b, "persistent" if int(r["majors"]) & 4 else "plain-launch")][0] += float(r["ms"])
+        bucket[(kind, b, "persistent" if int(r["majors"]) & 4 else "plain-launch")][1] += 1
+    for k, (ms, cnt) in sorted(bucket.items()):
+        print(f"   bucket {k}: {ms:8.3f} ms over {cnt} launches")
     print("  ms     n   TF/s  lost_ms(@1300)  kind maj M N K bn nz split H")
-    for k, (ms, fl, cnt) in sorted(agg.items(), key=lambda kv: -(kv[1][0] - kv[1][1] / 1.3e12))[:40]:
+    for k, (ms, fl, cnt) in sorted(agg.items(), key=lambda kv: -(kv[1][0] - kv[1][1] / 1.3e12))[:int(os.environ.get('MDM_REPORT_TOP', '25'))]:
         print(f"{ms:7.2f} {cnt:4d} {fl/ms/1e9:6.0f} {ms - fl/1.3e12:8.2f}   {' '.join(k)}")
 
 if __name__ == "__main__":

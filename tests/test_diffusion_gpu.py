@@ -223,16 +223,18 @@ def test_dynamic_threshold_reverse_step_and_sampling(mode):
     xc = [(xi * 3).cuda() for xi in x]      # large x_t: the quantile bound is active (> 1)
     lmc, mc_ = lm.cuda(), mask.cuda()
     with torch.no_grad():
+        times = torch.full((2,), 499, dtype=torch.long, device="cuda")
+        preds = m(xc, times, lmc, mc_, {})   # ONE evaluation feeds both sides (two runs differ by fp32-atomic order)
+        gam = dref.gammas_f32("DEEPFLOYD", 1000)
+        for xi, p, s in zip(xc, preds, [4, 1]):
+            a, b = smp._step_level(xi, p, 500, 480, s, True, 0.0, 1.0)
+            tab = dref.shift_table(gam, s, 1)
+            r0, rs = dref.reverse_step(xi.cpu(), p.cpu(), tab[500], tab[480], dref.V_PREDICTION, mode, 1.0, 0.0, True)
+            assert float(r0.abs().max()) <= 1.0 + 1e-6
+            assert nc.rel(a.cpu(), r0) <= 2e-6 and nc.rel(b.cpu(), rs) <= 2e-6
         x0, xs, _ = smp.get_xt_minus_1(m, 500, [a.clone() for a in xc], lmc, mc_, {}, time_step_last=480, ddim_eta=0.0,
                                        return_details=True)
-        times = torch.full((2,), 499, dtype=torch.long, device="cuda")
-        preds = m(xc, times, lmc, mc_, {})
-    gam = dref.gammas_f32("DEEPFLOYD", 1000)
-    for xi, p, s, a, b in zip(xc, preds, [4, 1], x0, xs):
-        tab = dref.shift_table(gam, s, 1)
-        r0, rs = dref.reverse_step(xi.cpu(), p.cpu(), tab[500], tab[480], dref.V_PREDICTION, mode, 1.0, 0.0, True)
-        assert float(r0.abs().max()) <= 1.0 + 1e-6
-        assert nc.rel(a.cpu(), r0) <= 2e-6 and nc.rel(b.cpu(), rs) <= 2e-6
+        assert all(float(a.abs().max()) <= 1.0 + 1e-6 for a in x0)
     # clip_sample on a bare tensor (reference surface)
     t = (torch.randn(2, 3, 16, 16) * 2).cuda()
     assert nc.rel(smp.clip_sample(t, 2.0).cpu(), dref.clip_sample(t.cpu(), 2.0, mode)) <= 1e-6
@@ -240,3 +242,41 @@ def test_dynamic_threshold_reverse_step_and_sampling(mode):
     out = pipe.sample(2, {"lm_outputs": lmc, "lm_mask": mc_}, 32, torch.device("cuda"), num_inference_steps=3,
                       ddim_eta=0.0, resample_steps=True)
     assert out.shape == (2, 3, 32, 32) and bool(torch.isfinite(out).all()) and float(out.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("kind", ["unet", "nested"])
+def test_get_loss_from_raw_reader_batch_uint8_and_unmasked_t5(kind):
+    """Input side of the path: get_loss fed the raw reader batch -- uint8 NHWC images and T5
+    features not yet multiplied by their mask -- must equal get_loss fed what clis/train_parallel.py:193-199 and
+    language_models/factory.py:101 prepare from it ((x - 127) / 128, permute, lm * mask) with the same draws."""
+    pipe, _, _, _, x, lm, mask, nested = pipeline(kind)
+    R = 32 if nested else 16
+    g = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (2, R, R, 3), generator=g, dtype=torch.uint8).cuda()
+    mask = mask.clone()
+    mask[0, 4:] = 0
+    mask[1, 2:] = 0
+    lm_raw, mask = lm.cuda(), mask.cuda()
+    images = torch.permute((u8.float() - 127.0) / 128.0, (0, 3, 1, 2)).contiguous()   # train_parallel.py:194-195
+    lm_masked = lm_raw * mask.unsqueeze(-1)                                           # factory.py:101
+    pipe.train()
+    vm = pipe.get_model().vision_model
+
+    def run(sample):
+        torch.manual_seed(77)
+        loss, time, x_t, pred, tgt, _ = pipe.get_loss(sample)
+        loss.mean().backward()
+        grads = {k: p.grad.detach().clone() for k, p in vm.named_parameters()}
+        vm.zero_grad(set_to_none=True)
+        return loss.detach(), time, x_t, tgt, grads
+
+    la, ta, xa, tga, ga = run({"images": images, "lm_outputs": lm_masked, "lm_mask": mask})
+    lb, tb, xb, tgb, gb = run({"image": u8, "lm_outputs": lm_raw, "lm_mask": mask, "lm_mask_applied": False})
+    assert torch.equal(ta, tb)
+    assert torch.equal(xa, xb) and torch.equal(tga, tgb), "fused uint8 q-sample must be bit-identical"
+    assert nc.rel(lb, la) <= 1e-3           # two engine runs differ by fp32-atomic order only
+    mags = sorted(float(v.abs().max()) for v in ga.values())
+    floor = 1e-2 * mags[len(mags) // 2]
+    for k in ga:
+        assert float((gb[k] - ga[k]).abs().max()) <= 5e-3 * max(float(ga[k].abs().max()), floor), k
+    assert vm.fuse_lm_mask is False
