@@ -153,6 +153,8 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if self.world > 1:
+            if os.environ.get("MDM_OVERLAP") is not None and int(os.environ.get("MDM_SM_RESERVE", "0")) > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", os.environ["MDM_SM_RESERVE"])  # the SMs the GEMMs leave free
             dist.init_process_group("nccl", init_method="env://")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
@@ -202,7 +204,8 @@ def measure_train(ctx, cfg_name, B, steps, warmup, headline=False, mixed_ratio=N
     vm = pipe.get_model().vision_model
     host = synthetic_host_batch(cfg_name, B, 1234 + ctx.rank)
     resident = {k: v.to(ctx.dev) for k, v in host.items()}
-    overlap = (parallel.GradientOverlap(vm, bucket_mb=int(os.environ.get("MDM_BUCKET_MB", "64")))
+    overlap = (parallel.GradientOverlap(vm, bucket_mb=int(os.environ.get("MDM_BUCKET_MB", "64")),
+                                        sm_reserve=int(os.environ.get("MDM_SM_RESERVE", "0")))
                if ctx.world > 1 and os.environ.get("MDM_OVERLAP") is not None else None)
 
     def step(sample):

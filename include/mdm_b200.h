@@ -72,6 +72,9 @@ typedef struct mdm_gemm_params {
   int32_t atomic;
   int32_t epi_tma; /* filled by the launcher: staged shared-memory + TMA-store epilogue in use */
   const void* gelu_grad_src; /* optional __half*, indexed like the output: result *= gelu'(src) (FFN backward) */
+  int32_t kfactor; /* MDM_GEMM_CONV_WGRAD only: pixel rows per pipeline stage = 64 * kfactor (0/1: 64). Narrow layers
+                    * (<= 64 channels) move only 4-8 KB per 64-pixel stage, so the stage round trip, not HBM, sets
+                    * the pace; 256-pixel stages cut the round trips four-fold. Needs a PW x PH = 64 * kfactor patch. */
 } mdm_gemm_params;
 
 /* Measurement aid for bench.py's roofline leg: while enabled every launch of the tcgen05 GEMM kernel
@@ -162,12 +165,16 @@ typedef struct mdm_net_io {
  * signature (batch, per-level batch, resolutions, tokens, mask/micro presence, save_for_backward) runs eagerly, the
  * second is captured and later ones replay the captured graphs: inputs / output gradients are copied into static
  * buffers, ONE graph launch runs the ~1-2.5 k kernels of the pass, outputs are copied out. Gradient-ready
- * notifications (mdm_net_set_grad_ready) do not fire for replayed backwards. Rebinding parameters or gradients drops
- * the recorded graphs. */
+ * notifications (mdm_net_set_grad_ready) keep working: the backward is then recorded as one graph per reported range
+ * and fn is called between the segment launches. Rebinding parameters or gradients drops the recorded graphs. */
 int mdm_net_set_graph_mode(mdm_net* net, int enable);
 /* Number of graph launches issued by this library since load; kernels inside replayed graphs are included in
  * mdm_launch_count(). */
 unsigned long long mdm_graph_launch_count(void);
+
+/* Leave `sms` of the 148 SMs to a concurrently running collective: the persistent GEMM kernels launch 148 - sms CTAs
+ * (process-wide; 0 restores the full grid). Used with the overlapped gradient all-reduce (NCCL_MAX_CTAS = sms). */
+int mdm_set_sm_reserve(int sms);
 
 /* UNet.forward / NestedUNet.forward (unet.py:971-987). */
 int mdm_net_forward(mdm_net* net, const mdm_net_io* io, mdm_stream_t stream);

@@ -265,7 +265,11 @@ void Engine::conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int l
   GemmParams p{};
   p.kind = GEMM_CONV_WGRAD;
   p.M = Cout; p.N = Cin;
-  conv_geom(p, N, H, W, 64);
+  // <= 64 channels on both sides: 256-pixel stages (gemm_tc.cu, kfactor). MDM_WGRAD_KFACTOR=1 restores 64.
+  static const int kf_env = getenv("MDM_WGRAD_KFACTOR") ? atoi(getenv("MDM_WGRAD_KFACTOR")) : 4;
+  const int kf = (Cout <= 64 && Cin <= 64 && H >= 16 && W >= 16 && kf_env > 1) ? kf_env : 1;
+  p.kfactor = kf;
+  conv_geom(p, N, H, W, 64 * kf);
   const long long mt = (Cout + 127) / 128;
   p.block_n = Cin >= 256 ? 256 : round16(Cin);
   p.nz1 = 9;

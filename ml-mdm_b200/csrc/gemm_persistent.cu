@@ -17,6 +17,8 @@
 namespace mdm {
 using namespace ptx;
 
+int g_sm_reserve = 0;
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -420,7 +422,10 @@ int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   p.num_stages = stages;
   const size_t smem = static_cast<size_t>(staging) + static_cast<size_t>(stages) * stage_bytes + 1024;
   const int num_tiles = m_tiles * n_tiles * p.nz1 * p.nz2;
-  const int grid = num_tiles < 148 ? num_tiles : 148;
+  // g_sm_reserve SMs are left to a concurrently running collective (mdm_set_sm_reserve): with a static tile stride a
+  // CTA that cannot become resident would otherwise serialise its whole share of tiles behind the others
+  const int sms = 148 - g_sm_reserve;
+  const int grid = num_tiles < sms ? num_tiles : sms;
   if (!a_mn && !b_mn) return launch_p<false, false>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
   if (!a_mn && b_mn) return launch_p<false, true>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
   if (a_mn && b_mn) return launch_p<true, true>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);

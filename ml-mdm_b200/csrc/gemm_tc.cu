@@ -52,8 +52,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   const int nb_alloc = B_MN ? ((p.block_n + 63) / 64) * 64 : p.block_n;
-  const int b_stage_bytes = nb_alloc * 128;
-  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  // weight gradients of narrow layers: kf x 64 pixel rows per stage, and a single A slab when M <= 64
+  const int kf = (p.kind == GEMM_CONV_WGRAD && p.kfactor > 1) ? p.kfactor : 1;
+  const int slab_bytes = SLAB_BYTES * kf;
+  const int a_slabs = (kf > 1 && p.M <= 64) ? 1 : 2;
+  const int a_stage_bytes = kf > 1 ? a_slabs * slab_bytes : A_STAGE_BYTES;
+  const int b_stage_bytes = nb_alloc * 128 * kf;
+  const int stage_bytes = a_stage_bytes + b_stage_bytes;
   const int nstages = p.num_stages;
 
   // ---- block coordinates
@@ -112,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb = kb_begin + i;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sA = smem + stage * stage_bytes;
-      uint8_t* sB = sA + A_STAGE_BYTES;
+      uint8_t* sB = sA + a_stage_bytes;
       uint64_t* bar = &full_bar[stage];
       mbar_expect_tx(bar, static_cast<uint32_t>(stage_bytes));
       if (p.kind == GEMM_PLAIN) {
@@ -149,9 +154,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kh = (p.taps == 9) ? z1 / 3 : 1;
         const int kw = (p.taps == 9) ? z1 % 3 : 1;
         tma_load_4d(sA, &tmA, bar, m0, ptw * p.PW, pth * p.PH, pimg);
-        tma_load_4d(sA + SLAB_BYTES, &tmA, bar, m0 + 64, ptw * p.PW, pth * p.PH, pimg);
+        if (a_slabs == 2) tma_load_4d(sA + slab_bytes, &tmA, bar, m0 + 64, ptw * p.PW, pth * p.PH, pimg);
         for (int s = 0; s < nslab_b; ++s)
-          tma_load_4d(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, ptw * p.PW + kw - 1,
+          tma_load_4d(sB + s * slab_bytes, &tmB, bar, n0 + 64 * s, ptw * p.PW + kw - 1,
                       pth * p.PH + kh - 1, pimg);
       }
       if (++stage == nstages) {
@@ -168,14 +173,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
-      const uint32_t b_base = a_base + A_STAGE_BYTES;
+      const uint32_t b_base = a_base + a_stage_bytes;
+      if (kf == 1) {
 #pragma unroll
-      for (int k = 0; k < BLOCK_K / 16; ++k) {
-        const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, SLAB_BYTES, 1024)
-                                    : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-        const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
-                                    : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-        umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, SLAB_BYTES, 1024)
+                                      : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
+                                      : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+      } else {
+        // tall MN-major slabs (kf * 64 pixel rows x 64 columns). With one A slab (M <= 64) the second 64-column
+        // block of A re-reads the first (leading-dimension offset 0): accumulator rows 64..127 are never stored.
+        const uint32_t a_lbo = a_slabs == 2 ? static_cast<uint32_t>(slab_bytes) : 0u;
+        for (int k = 0; k < 4 * kf; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(a_base + k * 2048, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 2048, static_cast<uint32_t>(slab_bytes), 1024);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
       }
       umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
       if (++stage == nstages) {
@@ -522,11 +538,20 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   if (encode_tmap(&tmB, B) != 0) return -21;
 
   const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
-  const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
+  if (p.kind != GEMM_CONV_WGRAD || p.kfactor < 1) p.kfactor = 1;
+  const int kf = p.kfactor;
+  if (kf > 1 && (!a_mn || !b_mn || p.PW * p.PH != 64 * kf || kf > 4)) return -15;
+  const int stage_bytes = kf > 1 ? ((p.M <= 64 ? 1 : 2) + nb_alloc / 64) * SLAB_BYTES * kf : A_STAGE_BYTES + nb_alloc * 128;
   static const int budget_kb = getenv("MDM_SMEM_BUDGET_KB") ? atoi(getenv("MDM_SMEM_BUDGET_KB")) : 0;  // dev knob
-  static const int narrow_kb = getenv("MDM_SMEM_NARROW_KB") ? atoi(getenv("MDM_SMEM_NARROW_KB")) : 0;      // dev knob
+  // Narrow tiles (N <= 64: the 32/64-channel levels of the 256- and 1024-px nests) do so little work per tile that
+  // the fixed per-tile latencies dominate; three co-resident CTAs of the one-tile-per-CTA form hide them better than
+  // the persistent form or two fat CTAs. Measured (profiles/r02_narrow_tile_knobs.txt): 3x3 convs with N <= 64 of a
+  // cc12m_256x256 step 11.0 ms persistent -> 9.7 ms one-tile form -> 7.0 ms with a 64 KB budget (8.4 ms at 44 KB);
+  // weight gradients prefer the deep pipeline and keep the full budget.
+  static const int narrow_kb = getenv("MDM_SMEM_NARROW_KB") ? atoi(getenv("MDM_SMEM_NARROW_KB")) : 64;
   int budget = budget_kb > 0 ? budget_kb * 1024 : SMEM_BUDGET;
-  if (narrow_kb > 0 && p.block_n <= 64) budget = narrow_kb * 1024;  // more co-resident CTAs for narrow tiles
+  if (narrow_kb > 0 && p.block_n <= 64 && p.kind != GEMM_CONV_WGRAD) budget = narrow_kb * 1024;
+  if (kf > 1) budget = 200 * 1024;  // tall stages: one CTA per SM, three 64 KB stages
   int stages = (budget - 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int per = (p.num_kblocks + p.nsplit - 1) / p.nsplit;
@@ -602,7 +627,7 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   {
     const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
     const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
-    static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 0;  // dev knob
+    static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 96;
     if (persistent && p.block_n >= persist_min_n && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
       return launch_gemm_persistent(tmA, tmB, tmO, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }

@@ -44,6 +44,7 @@ int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 
 // Counts kernel launches issued by this library (bench.py reports it as gpu_launches).
 extern unsigned long long g_launch_count;
+extern int g_sm_reserve;  // SMs the persistent kernels leave free (mdm_set_sm_reserve)
 extern bool g_profile;
 extern std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
 extern std::vector<mdm_gemm_params> g_profile_params;

@@ -1547,7 +1547,12 @@ struct Net {
     long long* times = nullptr;
     float *lm = nullptr, *mask = nullptr, *micro = nullptr;
     size_t lm_bytes = 0, mask_bytes = 0;
-    cudaGraphExec_t fwd = nullptr, bwd = nullptr;
+    cudaGraphExec_t fwd = nullptr;
+    // backward: one graph, or -- with a gradient-ready callback installed -- one graph per reported range, so the
+    // caller's collective on range i is enqueued right after segment i and overlaps segments i+1..
+    std::vector<cudaGraphExec_t> bwd;
+    std::vector<std::pair<uintptr_t, uintptr_t>> bwd_ranges;  // (lo, hi) reported after segment i; (0, 0): none
+    bool bwd_notifies = false;
     unsigned long long fwd_kernels = 0, bwd_kernels = 0;
     int dout_mask = 0;
     int seen = 0;
@@ -1562,8 +1567,10 @@ struct Net {
 
   void drop_graph(GraphRec& r) {
     if (r.fwd != nullptr) cudaGraphExecDestroy(r.fwd);
-    if (r.bwd != nullptr) cudaGraphExecDestroy(r.bwd);
-    r.fwd = r.bwd = nullptr;
+    for (cudaGraphExec_t g : r.bwd) cudaGraphExecDestroy(g);
+    r.fwd = nullptr;
+    r.bwd.clear();
+    r.bwd_ranges.clear();
   }
   void free_rec(GraphRec& r) {
     drop_graph(r);
@@ -1668,7 +1675,7 @@ struct Net {
     eng.st = st;
     prepare_weights();  // outside the graph: only runs when the fp32 masters changed
     const bool valid = r.fwd != nullptr && r.bind_epoch == bind_epoch && r.pool_epoch == eng.pool.epoch() &&
-                       (!r.training || r.bwd != nullptr);
+                       (!r.training || (!r.bwd.empty() && r.bwd_notifies == (ready_fn != nullptr)));
     if (!valid) {
       drop_graph(r);
       if (cap_st == nullptr) MDM_CUDA(cudaStreamCreateWithFlags(&cap_st, cudaStreamNonBlocking));
@@ -1721,23 +1728,34 @@ struct Net {
       MDM_CUDA(cudaMemcpyAsync(r.dout[l], gio->dout[l], r.x_bytes[l] / cfg.in_channels * cfg.out_channels,
                                cudaMemcpyDeviceToDevice, st));
     }
-    if (r.bwd == nullptr) {
+    if (r.bwd.empty()) {
       MDM_CHECK(have_tape, "graph mode: no recorded tape for this backward");
       mdm_net_grad_io sg{};
       for (int l = 0; l < cfg.num_levels; ++l) sg.dout[l] = (mask >> l) & 1 ? r.dout[l] : nullptr;
       const unsigned long long k0 = g_launch_count;
       MDM_CUDA(cudaStreamBeginCapture(cap_st, cudaStreamCaptureModeRelaxed));
       try {
+        // a reported range closes the current segment: its graph ends here and the next one begins
+        seg_cut = [&](uintptr_t lo, uintptr_t hi) {
+          r.bwd.push_back(end_capture());
+          r.bwd_ranges.emplace_back(lo, hi);
+          MDM_CUDA(cudaStreamBeginCapture(cap_st, cudaStreamCaptureModeRelaxed));
+        };
         backward_body(&sg, cap_st);
-        r.bwd = end_capture();
+        seg_cut = nullptr;
+        r.bwd.push_back(end_capture());
+        r.bwd_ranges.emplace_back(0, 0);
       } catch (...) {
+        seg_cut = nullptr;
         abort_capture();
+        drop_graph(r);
         eng.st = st;
         throw;
       }
       r.bwd_kernels = g_launch_count - k0;
       g_launch_count = k0;
       r.dout_mask = mask;
+      r.bwd_notifies = ready_fn != nullptr;
       eng.st = st;
       if (r.pool_epoch != eng.pool.epoch()) {  // the pool grew by freeing cached blocks: addresses in the forward graph died
         drop_graph(r);
@@ -1747,10 +1765,16 @@ struct Net {
       MDM_CHECK(mask == r.dout_mask, "graph mode: the set of output gradients changed between steps");
       MDM_CHECK(r.bind_epoch == bind_epoch, "graph mode: parameters or gradients were rebound between forward and backward");
     }
-    MDM_CUDA(cudaGraphLaunch(r.bwd, st));
+    for (size_t i = 0; i < r.bwd.size(); ++i) {
+      MDM_CUDA(cudaGraphLaunch(r.bwd[i], st));
+      ++g_graph_launches;
+      if (r.bwd_ranges[i].second > r.bwd_ranges[i].first && ready_fn != nullptr)
+        ready_fn(ready_user, reinterpret_cast<void*>(r.bwd_ranges[i].first), reinterpret_cast<void*>(r.bwd_ranges[i].second));
+    }
     g_launch_count += r.bwd_kernels;
-    ++g_graph_launches;
   }
+
+  std::function<void(uintptr_t, uintptr_t)> seg_cut;  // set while a segmented backward is being captured
 
   void replay_tape() {
     const int n = static_cast<int>(eng.tape.size());
@@ -1761,8 +1785,8 @@ struct Net {
       arena_lo = std::min(arena_lo, a);
       arena_hi = std::max(arena_hi, a + static_cast<uintptr_t>(p.numel) * sizeof(float));
     }
-    const bool notify = ready_fn != nullptr && static_cast<int>(learned.size()) == n && n > 0 && arena_hi > arena_lo &&
-                        eng.st != cap_st;  // a captured backward is replayed without host code: nothing to notify
+    // (while a backward is being captured the report cuts the graph into segments instead: see backward())
+    const bool notify = ready_fn != nullptr && static_cast<int>(learned.size()) == n && n > 0 && arena_hi > arena_lo;
     std::vector<uintptr_t> hi_prefix;  // highest gradient end address touched by closures 0..i
     if (notify) {
       hi_prefix.assign(n, arena_lo);
@@ -1808,7 +1832,8 @@ struct Net {
         const uintptr_t x = i > 0 ? hi_prefix[i - 1] : arena_lo;
         if (x < prev && (prev - x >= ready_min_bytes || i == 0)) {
           final_lo = x;
-          ready_fn(ready_user, reinterpret_cast<void*>(x), reinterpret_cast<void*>(prev));
+          if (seg_cut) seg_cut(x, prev);
+          else ready_fn(ready_user, reinterpret_cast<void*>(x), reinterpret_cast<void*>(prev));
           prev = x;
         }
       }
@@ -1908,6 +1933,11 @@ int mdm_net_set_graph_mode(mdm_net* net, int enable) {
 }
 
 unsigned long long mdm_graph_launch_count(void) { return mdm::g_graph_launches; }
+
+int mdm_set_sm_reserve(int sms) {
+  mdm::g_sm_reserve = sms < 0 ? 0 : (sms > 64 ? 64 : sms);
+  return 0;
+}
 
 int mdm_net_weights_changed(mdm_net* net) {
   net->net.weights_dirty = true;

@@ -185,8 +185,8 @@ class NativeNet:
         self._keep = None
         self.apply_lm_mask = False
         # CUDA-graph replay of forward / backward (mdm_net_set_graph_mode): on unless MDM_NO_GRAPH is set; switched
-        # off for this net by gradient accumulation (a fresh arena per backward would re-record every step) and while
-        # a gradient-ready callback is installed (replayed backwards run no host code)
+        # off for this net by gradient accumulation (a fresh arena per backward would re-record every step). With a
+        # gradient-ready callback installed the backward is recorded as one graph per reported range.
         self.graphs = os.environ.get("MDM_NO_GRAPH") is None
         self.lib.mdm_net_set_graph_mode(self.handle, int(self.graphs))
 
@@ -389,10 +389,7 @@ class NativeNet:
         if fn is None:
             self._ready_cb = None
             _lib.check(self.lib.mdm_net_set_grad_ready(self.handle, None, None, C.c_uint64(0)), "set_grad_ready")
-            if os.environ.get("MDM_NO_GRAPH") is None:
-                self.set_graph_mode(True)
             return
-        self.set_graph_mode(False)
         cb = _lib.GRAD_READY_FN(lambda user, lo, hi: fn(int(lo or 0), int(hi or 0)))
         self._ready_cb = cb  # keep the trampoline alive as long as the engine may call it
         _lib.check(self.lib.mdm_net_set_grad_ready(self.handle, cb, None, C.c_uint64(int(min_bytes))), "set_grad_ready")

@@ -59,8 +59,12 @@ class GradientOverlap:
     finish() reduces whatever was not reported (everything, on the first step, while the engine learns
     which closure touches which parameter) and makes the current stream wait for all collectives."""
 
-    def __init__(self, module, group=None, average=True, bucket_mb=64):
+    def __init__(self, module, group=None, average=True, bucket_mb=64, sm_reserve=0):
+        """sm_reserve: SMs the engine's persistent GEMM kernels leave free for the collective's CTAs
+        (mdm_set_sm_reserve); pair it with NCCL_MAX_CTAS=<sm_reserve> in the environment before the process group is
+        created, otherwise NCCL's CTAs and the one-CTA-per-SM GEMM queue behind each other."""
         self.module, self.group, self.average = module, group, average
+        self.sm_reserve = int(sm_reserve)
         self.works, self.low = [], None
         self.armed = False
         self.laid_out = False
@@ -70,10 +74,14 @@ class GradientOverlap:
         self.native = native
         if self.enabled and native is not None:
             native.set_grad_ready(self._on_ready, int(bucket_mb) << 20)
+            if self.sm_reserve > 0:
+                native.lib.mdm_set_sm_reserve(self.sm_reserve)
 
     def close(self):
         if self.native is not None:
             self.native.set_grad_ready(None)
+            if self.sm_reserve > 0:
+                self.native.lib.mdm_set_sm_reserve(0)
 
     def _reduce(self, t, async_op):
         world = dist.get_world_size(self.group)

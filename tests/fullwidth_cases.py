@@ -120,6 +120,7 @@ def run_case(name, B=1, S=8, micro=False, verbose=False):
     rep = {"out": [(rel(a, r), rel(b, r)) for a, b, r in zip(oo, o32, o64)], "grads": {}, "seconds": tm,
            "missing": [k for k in g64 if k not in go]}
     rep["grad_absmax"] = {k: float(go[k].abs().max()) for k in go}
+    rep["grad_absmax_tf32"] = {k: float(g32[k].abs().max()) for k in g32}
     mags = sorted(float(r.abs().max()) for r in g64.values())
     rep["grad_typical"] = mags[len(mags) // 2]  # median over parameters of max|d loss / d parameter|
     for k, r in g64.items():

@@ -156,7 +156,7 @@ def run_conv_dgrad(nimg, H, W, Cin, Cout, block_n, seed=0):
     return {"f32": rel_err(out, ref)}
 
 
-def run_conv_wgrad(nimg, H, W, Cin, Cout, block_n, nsplit=1, seed=0):
+def run_conv_wgrad(nimg, H, W, Cin, Cout, block_n, nsplit=1, seed=0, kfactor=1):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = (torch.randn(nimg, H, W, Cin, generator=g) * 0.5).to(torch.float16).to(DEV)
     dy = (torch.randn(nimg, H, W, Cout, generator=g) * 0.5).to(torch.float16).to(DEV)
@@ -164,11 +164,12 @@ def run_conv_wgrad(nimg, H, W, Cin, Cout, block_n, nsplit=1, seed=0):
                                       dy.float().permute(0, 3, 1, 2), padding=1)  # OIHW
     ref = ref.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
     PW = conv_geometry(H, W)
-    PH = 64 // PW
+    PH = 64 * kfactor // PW
     sa = _lib.tmap(dy.data_ptr(), (Cout, W, H, nimg), (1, Cout, W * Cout, H * W * Cout), (64, PW, PH, 1))
     sb = _lib.tmap(x.data_ptr(), (Cin, W, H, nimg), (1, Cin, W * Cin, H * W * Cin), (64, PW, PH, 1))
     p = _lib.GemmParams()
     p.kind = 2
+    p.kfactor = kfactor
     p.M, p.N = Cout, Cin
     p.block_n = block_n
     p.H, p.W, p.PW, p.PH = H, W, PW, PH
@@ -216,6 +217,11 @@ CASES = [
     ("conv_dgrad_mix", lambda: run_conv_dgrad(1, 32, 32, 64, 192, 64)),
     ("conv_wgrad_16", lambda: run_conv_wgrad(2, 16, 16, 128, 128, 128)),
     ("conv_wgrad_split", lambda: run_conv_wgrad(4, 32, 32, 64, 256, 64, nsplit=4)),
+    # narrow layers (the 32/64-channel levels of the 256/1024-px nests): 256-pixel stages, one A slab when M <= 64
+    ("conv_wgrad_tall_c32", lambda: run_conv_wgrad(2, 64, 64, 32, 32, 32, nsplit=4, kfactor=4)),
+    ("conv_wgrad_tall_c64", lambda: run_conv_wgrad(3, 32, 48, 64, 64, 64, nsplit=3, kfactor=4)),
+    ("conv_wgrad_tall_c32_64", lambda: run_conv_wgrad(1, 48, 32, 32, 64, 32, nsplit=1, kfactor=4)),
+    ("conv_wgrad_tall_c96_32", lambda: run_conv_wgrad(2, 32, 32, 32, 96, 32, nsplit=2, kfactor=2)),
 ]
 
 TOL = {"f32": 2e-5, "f16": 1.5e-3, "act": 1.5e-3}

@@ -125,19 +125,25 @@ def test_grad_ready_ranges_are_final(kind):
     model.zero_grad(set_to_none=True)
     assert native.optimize_arena_layout()   # arena re-sorted by gradient finalisation order
     native.set_grad_ready(on_ready, native_bytes_hint)
-    step()
+    arena = None
+    # second backward: recorded as one CUDA graph per reported range (graph mode) or run eagerly (MDM_NO_GRAPH);
+    # third and fourth: replayed segment by segment with the callback between the launches
+    for rnd in range(3):
+        snaps.clear()
+        model.zero_grad(set_to_none=True)
+        step()
+        assert len(snaps) >= 3, "no gradient range was reported during backward %d" % (rnd + 2)
+        arena = native.grad_arena
+        covered = 0
+        prev_lo = max(off + p.numel() for p, off in zip(native.params, native.offsets))  # end of the last gradient
+        top = prev_lo
+        for a, b, snap in snaps:
+            assert b == prev_lo, "ranges must tile the arena from the top down without gaps or overlap"
+            prev_lo = a
+            covered += b - a
+            assert torch.equal(snap, arena[a:b]), f"gradient range [{a},{b}) changed after it was reported final"
+        assert prev_lo == 0 and covered == top
     native.set_grad_ready(None)
-    assert len(snaps) >= 3, "no gradient range was reported during the second backward"
-    arena = native.grad_arena
-    covered = 0
-    prev_lo = max(off + p.numel() for p, off in zip(native.params, native.offsets))  # end of the last gradient
-    top = prev_lo
-    for a, b, snap in snaps:
-        assert b == prev_lo, "ranges must tile the arena from the top down without gaps or overlap"
-        prev_lo = a
-        covered += b - a
-        assert torch.equal(snap, arena[a:b]), f"gradient range [{a},{b}) changed after it was reported final"
-    assert prev_lo == 0 and covered == top
     # gradients handed to autograd alias the arena (adopted, not cloned)
     lo_b, hi_b = arena.data_ptr(), arena.data_ptr() + 4 * arena.numel()
     assert all(lo_b <= p.grad.data_ptr() < hi_b for p in model.parameters())
