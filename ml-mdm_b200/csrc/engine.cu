@@ -221,8 +221,18 @@ static void conv_geom(GemmParams& p, int N, int H, int W, int pixels_per_tile) {
   p.nimg = N;
 }
 
+static const bool g_fold = getenv("MDM_NO_WFOLD") == nullptr;
+
 void Engine::conv3x3_fwd(const __half* x16, int ldx, int N, int H, int W, int Cin, const __half* w16, int Cout,
-                         const Epi& e) {
+                         const Epi& e, const __half* w16f, const float* bias_f) {
+  if (g_fold && w16f != nullptr && fold_ok(Cin, Cout) && ldx == Cin && (W & 1) == 0 && (e.ldc == 0 || e.ldc == Cout) &&
+      (e.bias == nullptr || bias_f != nullptr) && e.gelu_grad_src == nullptr) {
+    Epi f = e;
+    f.bias = e.bias != nullptr ? bias_f : nullptr;
+    f.ldc = 0;
+    conv3x3_fwd(x16, 2 * Cin, N, H, W / 2, 2 * Cin, w16f, 2 * Cout, f);
+    return;
+  }
   GemmParams p{};
   p.kind = GEMM_CONV;
   p.N = Cout; p.K = Cin;
@@ -241,7 +251,14 @@ void Engine::conv3x3_fwd(const __half* x16, int ldx, int N, int H, int W, int Ci
 }
 
 void Engine::conv3x3_dgrad(const __half* dy16, int ldy, int N, int H, int W, int Cout, const __half* w16, int Cin,
-                           const Epi& e) {
+                           const Epi& e, const __half* w16f) {
+  if (g_fold && w16f != nullptr && fold_ok(Cin, Cout) && ldy == Cout && (W & 1) == 0 && (e.ldc == 0 || e.ldc == Cin) &&
+      e.bias == nullptr && e.gelu_grad_src == nullptr) {
+    Epi f = e;
+    f.ldc = 0;
+    conv3x3_dgrad(dy16, 2 * Cout, N, H, W / 2, 2 * Cout, w16f, 2 * Cin, f);
+    return;
+  }
   GemmParams p{};
   p.kind = GEMM_CONV;
   p.N = Cin; p.K = Cout;
@@ -260,8 +277,12 @@ void Engine::conv3x3_dgrad(const __half* dy16, int ldy, int N, int H, int W, int
   run(a, b, 0, 1, p, e, mt * ((Cin + p.block_n - 1) / p.block_n), st);
 }
 
-void Engine::conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int Cin,
-                           int Cout, float* packed_out) {
+bool Engine::conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int Cin,
+                           int Cout, float* packed_out, bool allow_fold) {
+  if (g_fold && allow_fold && fold_ok(Cin, Cout) && ldy == Cout && ldx == Cin && (W & 1) == 0) {
+    conv3x3_wgrad(dy16, 2 * Cout, x16, 2 * Cin, N, H, W / 2, 2 * Cin, 2 * Cout, packed_out, false);
+    return true;
+  }
   GemmParams p{};
   p.kind = GEMM_CONV_WGRAD;
   p.M = Cout; p.N = Cin;
@@ -292,6 +313,7 @@ void Engine::conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int l
                     p.PW, p.PH, 1);
   const int rc = launch_gemm(a, b, 1, 1, p, st);
   if (rc != 0) throw MdmFail("tcgen05 conv wgrad launch failed, rc=" + std::to_string(rc));
+  return false;
 }
 
 }  // namespace mdm

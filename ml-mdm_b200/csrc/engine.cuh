@@ -75,6 +75,9 @@ struct Param {
   float* g = nullptr;  // bound fp32 gradient buffer (owned by the caller), may be null
   __half* w16 = nullptr;  // packed fp16 operand copy (owned by the engine), null if not a GEMM weight
   int pack = 0;           // 0 none, 1 plain cast, 2 conv [Co][taps][Ci], 3 conv_in [Co][32]
+  // narrow 3x3 convs (fold_ok): W-folded weights [2Co][9][2Ci] and the bias repeated twice (engine-owned)
+  __half* w16f = nullptr;
+  float* bias_f = nullptr;
 };
 
 struct Epi {
@@ -118,14 +121,19 @@ struct Engine {
   void gemm_nn(const __half* A, long long lda, const __half* Bm, long long ldb, int M, int N, int K, const Epi& e);
   // C[M,N] = At[K,M]^T * Bm[K,N]   (both MN-major; contraction over rows)
   void gemm_tn(const __half* At, long long lda, const __half* Bm, long long ldb, int M, int N, int K, const Epi& e);
-  // 3x3 / pad 1 / stride 1 conv over NHWC fp16 x (channel stride ldx), packed weights [Cout][9][Cin]
+  // 3x3 / pad 1 / stride 1 conv over NHWC fp16 x (channel stride ldx), packed weights [Cout][9][Cin].
+  // w16f / bias_f (optional): the layer's W-folded weights and doubled bias; when given and the tensors are dense and W
+  // is even the conv runs on the folded view (2Cin -> 2Cout over W/2): TMA moves one <= 128-byte row per pixel at a
+  // fixed rate, so 32-channel tensors (64-byte rows) otherwise run at half speed (profiles/r02_conv_micro.txt).
+  static bool fold_ok(int Cin, int Cout) { return Cin <= 64 && Cout <= 64 && (Cin <= 32 || Cout <= 32); }
   void conv3x3_fwd(const __half* x16, int ldx, int N, int H, int W, int Cin, const __half* w16, int Cout,
-                   const Epi& e);
+                   const Epi& e, const __half* w16f = nullptr, const float* bias_f = nullptr);
   void conv3x3_dgrad(const __half* dy16, int ldy, int N, int H, int W, int Cout, const __half* w16, int Cin,
-                     const Epi& e);
-  // packed_out: [Cout][9][Cin] fp32, overwritten
-  void conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int Cin,
-                     int Cout, float* packed_out);
+                     const Epi& e, const __half* w16f = nullptr);
+  // packed_out: [Cout][9][Cin] fp32, overwritten -- or, when `folded` (same conditions), [2Cout][9][2Cin] of the
+  // folded problem (to be un-folded by unpack_conv_wgrad_fold); returns whether the folded form was used
+  bool conv3x3_wgrad(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int Cin,
+                     int Cout, float* packed_out, bool allow_fold = false);
 };
 
 // Fused attention (attention.cu)

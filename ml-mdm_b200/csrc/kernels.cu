@@ -1108,6 +1108,46 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __half* __restri
     for (int t = 0; t < taps; ++t) p[(co * taps + t) * Ci + ci] = __float2half_rn(w[i * taps + t]);
   }
 }
+// W-folded weights of a 3x3 conv (see Engine::conv3x3_* in engine.cu): two horizontally adjacent pixels are treated as
+// one pixel with twice the channels, so a Ci -> Co conv over (H, W) becomes a 2Ci -> 2Co conv over (H, W/2) on the SAME
+// memory. Output column 2j+po reads input column 2(j+kwf-1)+pi through the original tap kw = 2(kwf-1)+pi-po+1 when
+// that is in 0..2, else through a zero. p: [2Co][9][2Ci] fp16, row (po*Co+co), tap kh*3+kwf, column pi*Ci+ci.
+__global__ void pack_conv_w_fold_kernel(const float* __restrict__ w, __half* __restrict__ p, int Co, int Ci) {
+  const long long total = 4ll * Co * Ci * 9;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gs = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += gs) {
+    const int col = static_cast<int>(i % (2 * Ci));
+    long long t = i / (2 * Ci);
+    const int tap = static_cast<int>(t % 9);
+    const int row = static_cast<int>(t / 9);
+    const int pi = col / Ci, ci = col - pi * Ci, po = row / Co, co = row - po * Co;
+    const int kh = tap / 3, kwf = tap - 3 * kh;
+    const int kw = 2 * (kwf - 1) + pi - po + 1;
+    float v = 0.f;
+    if (kw >= 0 && kw <= 2) v = w[(static_cast<long long>(co) * Ci + ci) * 9 + kh * 3 + kw];
+    p[i] = __float2half_rn(v);
+  }
+}
+// g [Co][Ci][3][3] += inv_scale * (the entries of the folded gradient packed [2Co][9][2Ci] that map to each tap)
+__global__ void unpack_conv_wgrad_fold_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci,
+                                              const float* __restrict__ inv_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Co * Ci * 9) return;
+  const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+  const int kh = tap / 3, kw = tap - 3 * kh;
+  float acc = 0.f;
+  for (int po = 0; po < 2; ++po)
+    for (int pi = 0; pi < 2; ++pi) {
+      const int num = kw - 1 - pi + po;  // = 2 (kwf - 1)
+      if (num & 1) continue;
+      const int kwf = num / 2 + 1;
+      if (kwf < 0 || kwf > 2) continue;
+      acc += packed[(static_cast<long long>(po * Co + co) * 9 + kh * 3 + kwf) * (2 * Ci) + pi * Ci + ci];
+    }
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+  g[i] += inv * acc;
+}
 __global__ void pack_conv_in_w_kernel(const float* __restrict__ w, __half* __restrict__ p, int Co, int Ci) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Co * 32) return;
@@ -1383,6 +1423,16 @@ void sample_inv_std(const float* x, float* inv_std, int N, long long per, cudaSt
 
 void pack_conv_w(const float* w_oihw, __half* packed, int Co, int Ci, int taps, cudaStream_t st) {
   pack_conv_w_kernel<<<grid_for(static_cast<long long>(Co) * Ci), 256, 0, st>>>(w_oihw, packed, Co, Ci, taps);
+  MDM_LAUNCHED();
+}
+void pack_conv_w_fold(const float* w_oihw, __half* packed, int Co, int Ci, cudaStream_t st) {
+  pack_conv_w_fold_kernel<<<grid_for(4ll * Co * Ci * 9), 256, 0, st>>>(w_oihw, packed, Co, Ci);
+  MDM_LAUNCHED();
+}
+void unpack_conv_wgrad_fold(const float* packed, float* g_oihw, int Co, int Ci, const float* inv_scale,
+                            cudaStream_t st) {
+  unpack_conv_wgrad_fold_kernel<<<static_cast<unsigned>(cdiv(static_cast<long long>(Co) * Ci * 9, 256)), 256, 0, st>>>(
+      packed, g_oihw, Co, Ci, inv_scale);
   MDM_LAUNCHED();
 }
 void pack_conv_in_w(const float* w_oihw, __half* packed, int Co, int Ci, cudaStream_t st) {

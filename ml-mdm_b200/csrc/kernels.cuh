@@ -126,6 +126,11 @@ void sample_inv_std(const float* x, float* inv_std, int N, long long per, cudaSt
 // ---- weight packing (fp32 master parameters -> fp16 operand layouts) and gradient unpacking
 void pack_conv_w(const float* w_oihw, __half* packed, int Co, int Ci, int taps, cudaStream_t st);
 void pack_conv_in_w(const float* w_oihw, __half* packed, int Co, int Ci, cudaStream_t st);  // [Co][32]
+// W-folded 3x3 weights [2Co][9][2Ci] (two adjacent pixels as one pixel with twice the channels) and the matching
+// gradient un-fold: g_oihw += inv_scale * fold^T(packed [2Co][9][2Ci])
+void pack_conv_w_fold(const float* w_oihw, __half* packed, int Co, int Ci, cudaStream_t st);
+void unpack_conv_wgrad_fold(const float* packed, float* g_oihw, int Co, int Ci, const float* inv_scale,
+                            cudaStream_t st);
 // g_oihw += inv_scale * packed  (packed: [Co][taps][ci_ld] fp32, only ci < Ci used)
 void unpack_conv_wgrad(const float* packed, float* g_oihw, int Co, int Ci, int taps, int ci_ld,
                        const float* inv_scale, cudaStream_t st);

@@ -349,7 +349,21 @@ struct Net {
         p.w16 = static_cast<__half*>(persist(sizeof(__half) * n));
       }
       if (p.pack == 1) cast_f32_to_f16(p.w, p.w16, p.numel, st);
-      else if (p.pack == 2) pack_conv_w(p.w, p.w16, static_cast<int>(p.shape[0]), static_cast<int>(p.shape[1]), 9, st);
+      else if (p.pack == 2) {
+        const int Co = static_cast<int>(p.shape[0]), Ci = static_cast<int>(p.shape[1]);
+        pack_conv_w(p.w, p.w16, Co, Ci, 9, st);
+        if (Engine::fold_ok(Ci, Co) && Co % 4 == 0) {  // narrow layer: W-folded copy + doubled bias (engine.cu)
+          if (p.w16f == nullptr) {
+            p.w16f = static_cast<__half*>(persist(sizeof(__half) * 36ull * Co * Ci));
+            p.bias_f = static_cast<float*>(persist(sizeof(float) * 2ull * Co));
+          }
+          pack_conv_w_fold(p.w, p.w16f, Co, Ci, st);
+          auto bi = pindex.find(p.name.substr(0, p.name.size() - 6) + "bias");  // "...weight" -> "...bias"
+          MDM_CHECK(bi != pindex.end() && plist[bi->second].w != nullptr, "conv bias not bound");
+          for (int r = 0; r < 2; ++r)
+            MDM_CUDA(cudaMemcpyAsync(p.bias_f + r * Co, plist[bi->second].w, sizeof(float) * Co, cudaMemcpyDeviceToDevice, st));
+        }
+      }
       else if (p.pack == 3) pack_conv_in_w(p.w, p.w16, static_cast<int>(p.shape[0]), static_cast<int>(p.shape[1]), st);
     }
     for (auto& L : levels) {
@@ -411,6 +425,15 @@ struct Net {
       if (acc_dx) e.residual = dx32;
       eng.gemm_nn(dy16, ldy, W.w16, K, M, K, N, e);
     }
+  }
+
+  // 3x3 weight gradient into w.g (+=): folded form for the narrow layers (engine.cu), else the plain one.
+  // wtmp must hold 36 * cin * cout floats.
+  void conv_wgrad_into(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int cin, int cout,
+                       float* wtmp, Param& w) {
+    const bool folded = eng.conv3x3_wgrad(dy16, ldy, x16, ldx, N, H, W, cin, cout, wtmp, w.w16f != nullptr);
+    if (folded) unpack_conv_wgrad_fold(wtmp, w.g, cout, cin, inv_scale(), eng.st);
+    else unpack_conv_wgrad(wtmp, w.g, cout, cin, 9, cin, inv_scale(), eng.st);
   }
 
   struct GnOut {
@@ -483,7 +506,7 @@ struct Net {
       Epi e;
       e.bias = c1b.w;
       e.out_f32 = h;
-      eng.conv3x3_fwd(g1.y16, cin, N, H, W, cin, c1w.w16, cout, e);
+      eng.conv3x3_fwd(g1.y16, cin, N, H, W, cin, c1w.w16, cout, e, c1w.w16f, c1w.bias_f);
     }
     Src2 hs{h, nullptr, cout, 0};
     GnOut g2 = gn_fwd(hs, N, HW, G, n2w, n2b, ls->film, L.film_total, r.film_off, 1, false);
@@ -504,7 +527,7 @@ struct Net {
       e.bias = c2b.w;
       e.residual = res;
       e.out_f32 = out->p;
-      eng.conv3x3_fwd(g2.y16, cout, N, H, W, cout, c2w.w16, cout, e);
+      eng.conv3x3_fwd(g2.y16, cout, N, H, W, cout, c2w.w16, cout, e, c2w.w16f, c2w.bias_f);
     }
     if (!eng.training) {
       eng.pool.release(g1.y16);
@@ -531,16 +554,14 @@ struct Net {
       float* bias_scratch = E.zeros_f32(cout);
       cast_colsum(out->g, d16, rows, cout, bias_scratch, inv_scale(), E.st);
       if (c2b.g != nullptr) axpy_f32(c2b.g, bias_scratch, 1.f, cout, 1, E.st);
-      float* wtmp = E.alloc<float>(9ll * cout * std::max(cin, cout));
-      if (c2w.g != nullptr) {
-        E.conv3x3_wgrad(d16, cout, g2.y16, cout, N, H, W, cout, cout, wtmp);
-        unpack_conv_wgrad(wtmp, c2w.g, cout, cout, 9, cout, inv_scale(), E.st);
-      }
+      float* wtmp = E.alloc<float>(std::max((Engine::fold_ok(cin, cout) ? 36ll : 9ll) * cin * cout,
+                                             (Engine::fold_ok(cout, cout) ? 36ll : 9ll) * cout * cout));
+      if (c2w.g != nullptr) conv_wgrad_into(d16, cout, g2.y16, cout, N, H, W, cout, cout, wtmp, c2w);
       __half* da2 = E.alloc<__half>(rows * cout);
       {
         Epi e;
         e.out_f16 = da2;
-        E.conv3x3_dgrad(d16, cout, N, H, W, cout, c2w.w16, cout, e);
+        E.conv3x3_dgrad(d16, cout, N, H, W, cout, c2w.w16, cout, e, c2w.w16f);
       }
       // norm2 + FiLM + SiLU: h has a single consumer, so its gradient goes straight to the fp16 operand
       // of conv1's backward, with conv1's bias gradient as column sums
@@ -561,15 +582,12 @@ struct Net {
         E.pool.release(dfilm);
       }
       // conv1
-      if (c1w.g != nullptr) {
-        E.conv3x3_wgrad(dh16, cout, g1.y16, cin, N, H, W, cin, cout, wtmp);
-        unpack_conv_wgrad(wtmp, c1w.g, cout, cin, 9, cin, inv_scale(), E.st);
-      }
+      if (c1w.g != nullptr) conv_wgrad_into(dh16, cout, g1.y16, cin, N, H, W, cin, cout, wtmp, c1w);
       __half* da1 = E.alloc<__half>(rows * cin);
       {
         Epi e;
         e.out_f16 = da1;
-        E.conv3x3_dgrad(dh16, cout, N, H, W, cout, c1w.w16, cin, e);
+        E.conv3x3_dgrad(dh16, cout, N, H, W, cout, c1w.w16, cin, e, c1w.w16f);
       }
       E.pool.release(dh16);
       // norm1 + SiLU -> x (and skip). Identity residual folds in as `extra`.
@@ -1040,7 +1058,7 @@ struct Net {
     e.bias = bb.w;
     e.residual = residual;
     e.out_f32 = y->p;
-    eng.conv3x3_fwd(x16, Cin, N, H, W, Cin, w.w16, Cout, e);
+    eng.conv3x3_fwd(x16, Cin, N, H, W, Cin, w.w16, Cout, e, w.w16f, w.bias_f);
     if (n_alloc > N) {
       const long long lead = static_cast<long long>(N) * H * W * Cout;
       MDM_CUDA(cudaMemsetAsync(y->p + lead, 0, sizeof(float) * (y->numel() - lead), eng.st));
@@ -1057,15 +1075,14 @@ struct Net {
     __half* d16 = E.alloc<__half>(rows * Cout);
     cast_colsum(y->g, d16, rows, Cout, bb.g, inv_scale(), E.st);
     if (w.g != nullptr) {
-      float* wtmp = E.alloc<float>(9ll * Cin * Cout);
-      E.conv3x3_wgrad(d16, Cout, x16, Cin, N, H, W, Cin, Cout, wtmp);
-      unpack_conv_wgrad(wtmp, w.g, Cout, Cin, 9, Cin, inv_scale(), E.st);
+      float* wtmp = E.alloc<float>((Engine::fold_ok(Cin, Cout) ? 36ll : 9ll) * Cin * Cout);
+      conv_wgrad_into(d16, Cout, x16, Cin, N, H, W, Cin, Cout, wtmp, w);
       E.pool.release(wtmp);
     }
     float* dx = E.alloc<float>(rows * Cin);
     Epi e;
     e.out_f32 = dx;
-    E.conv3x3_dgrad(d16, Cout, N, H, W, Cout, w.w16, Cin, e);
+    E.conv3x3_dgrad(d16, Cout, N, H, W, Cout, w.w16, Cin, e, w.w16f);
     E.pool.release(d16);
     return dx;
   }
@@ -1439,7 +1456,7 @@ struct Net {
       Epi e;
       e.bias = ob.w;
       e.out_f32 = o;
-      E.conv3x3_fwd(g.y16, Cf, B, R, R, Cf, ow.w16, oc, e);
+      E.conv3x3_fwd(g.y16, Cf, B, R, R, Cf, ow.w16, oc, e, ow.w16f, ow.bias_f);
       nhwc_to_nchw(o, oc, io->out[li], B, oc, HW, E.st);
       E.pool.release(o);
       outs[li].res = R;
