@@ -72,6 +72,8 @@ typedef struct mdm_gemm_params {
   int32_t atomic;
   int32_t epi_tma; /* filled by the launcher: staged shared-memory + TMA-store epilogue in use */
   const void* gelu_grad_src; /* optional __half*, indexed like the output: result *= gelu'(src) (FFN backward) */
+  int32_t cluster; /* filled by the launcher: CTAs per cluster along the M tiles (1, 2 or 4). The CTAs of a cluster work
+                    * on the same B (weight) tile: each fetches 1/cluster of it and TMA multicasts it to the others. */
   int32_t kfactor; /* MDM_GEMM_CONV_WGRAD only: pixel rows per pipeline stage = 64 * kfactor (0/1: 64). Narrow layers
                     * (<= 64 channels) move only 4-8 KB per 64-pixel stage, so the stage round trip, not HBM, sets
                     * the pace; 256-pixel stages cut the round trips four-fold. Needs a PW x PH = 64 * kfactor patch. */

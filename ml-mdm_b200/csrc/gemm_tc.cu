@@ -38,7 +38,8 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
-               const __grid_constant__ CUtensorMap tmOact, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmOact, const __grid_constant__ CUtensorMap tmBpart,
+               const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -72,6 +73,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_end = min(p.num_kblocks, kb_begin + per);
   const int nkb = kb_end - kb_begin;
 
+  // Cluster of cs CTAs along the M tiles: same B tile for all of them, each fetches 1/cs of it and multicasts.
+  // (TMA moves ~one <= 128-byte row per 3 clocks per SM whatever the row holds; a 128 x 256 tile needs 128 A + 256 B
+  // rows per k block against 512 clocks of MMA, so the loads, not the tensor pipe, set the pace without this.)
+  const int cs = p.cluster > 1 ? p.cluster : 1;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   const int m_tile = blockIdx.x;
   const int m0 = m_tile * BLOCK_M;
   const int n0 = blockIdx.y * p.block_n;
@@ -89,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(cs));  // one arrival per consumer CTA of the cluster
     }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
@@ -101,6 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // peers' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -127,7 +135,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_4d(sA, &tmA, bar, m0, kb * BLOCK_K, az1, az2);
           tma_load_4d(sA + SLAB_BYTES, &tmA, bar, m0 + 64, kb * BLOCK_K, az1, az2);
         }
-        if (!B_MN) {
+        if (cs > 1) {
+          if (!B_MN) {
+            const int rows = p.block_n / cs;
+            tma_load_4d_mc(sB + crank * rows * 128, &tmBpart, bar, kb * BLOCK_K, n0 + crank * rows, bz1, bz2, cmask);
+          } else {
+            for (int s = crank; s < nslab_b; s += cs)
+              tma_load_4d_mc(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, kb * BLOCK_K, bz1, bz2, cmask);
+          }
+        } else if (!B_MN) {
           tma_load_4d(sB, &tmB, bar, kb * BLOCK_K, n0, bz1, bz2);
         } else {
           for (int s = 0; s < nslab_b; ++s)
@@ -139,10 +155,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kh = (p.taps == 9) ? tap / 3 : 1;
         const int kw = (p.taps == 9) ? tap % 3 : 1;
         tma_load_4d(sA, &tmA, bar, cb * BLOCK_K, tw * p.PW + kw - 1, th * p.PH + kh - 1, img);
-        if (!B_MN) {
+        const int wt = p.flip ? (p.taps - 1 - tap) : tap;
+        if (cs > 1) {
+          if (!B_MN) {
+            const int rows = p.block_n / cs;
+            tma_load_4d_mc(sB + crank * rows * 128, &tmBpart, bar, cb * BLOCK_K, n0 + crank * rows, tap, 0, cmask);
+          } else {
+            for (int s = crank; s < nslab_b; s += cs)
+              tma_load_4d_mc(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, cb * BLOCK_K, wt, 0, cmask);
+          }
+        } else if (!B_MN) {
           tma_load_4d(sB, &tmB, bar, cb * BLOCK_K, n0, tap, 0);
         } else {
-          const int wt = p.flip ? (p.taps - 1 - tap) : tap;
           for (int s = 0; s < nslab_b; ++s)
             tma_load_4d(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, cb * BLOCK_K, wt, 0);
         }
@@ -155,9 +179,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kw = (p.taps == 9) ? z1 % 3 : 1;
         tma_load_4d(sA, &tmA, bar, m0, ptw * p.PW, pth * p.PH, pimg);
         if (a_slabs == 2) tma_load_4d(sA + slab_bytes, &tmA, bar, m0 + 64, ptw * p.PW, pth * p.PH, pimg);
-        for (int s = 0; s < nslab_b; ++s)
-          tma_load_4d(sB + s * slab_bytes, &tmB, bar, n0 + 64 * s, ptw * p.PW + kw - 1,
-                      pth * p.PH + kh - 1, pimg);
+        if (cs > 1) {
+          for (int s = crank; s < nslab_b; s += cs)
+            tma_load_4d_mc(sB + s * slab_bytes, &tmB, bar, n0 + 64 * s, ptw * p.PW + kw - 1, pth * p.PH + kh - 1, pimg,
+                           cmask);
+        } else {
+          for (int s = 0; s < nslab_b; ++s)
+            tma_load_4d(sB + s * slab_bytes, &tmB, bar, n0 + 64 * s, ptw * p.PW + kw - 1,
+                        pth * p.PH + kh - 1, pimg);
+        }
       }
       if (++stage == nstages) {
         stage = 0;
@@ -193,7 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
       }
-      umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+      // frees the smem slot once these MMAs retire -- in every CTA of the cluster, whose producers all write into it
+      if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);
+      else umma_commit(&empty_bar[stage]);
       if (++stage == nstages) {
         stage = 0;
         phase ^= 1;
@@ -217,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int pw = r - ph * p.PW;
     const int h = th * p.PH + ph;
     const int w = tw * p.PW + pw;
-    valid = (h < p.H) && (w < p.W);
+    valid = (h < p.H) && (w < p.W) && (img < p.nimg);  // (the grid is rounded up to whole clusters)
     row_off = (static_cast<long long>(img * p.H + h) * p.W + w) * p.ldc;
   } else {
     const int row = m0 + r;
@@ -442,6 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // no peer may still arrive on this CTA's barriers after it is gone
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -491,8 +524,8 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s, bool f32 = false) {
 }
 
 template <bool A_MN, bool B_MN>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const GemmParams& p, dim3 grid,
-                size_t smem, cudaStream_t stream) {
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap& tmBpart,
+                const GemmParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>,
@@ -506,7 +539,24 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     cudaEventCreate(&e1);
     cudaEventRecord(e0, stream);
   }
-  gemm_tc_kernel<A_MN, B_MN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], p);
+  if (p.cluster > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN>, tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  } else {
+    gemm_tc_kernel<A_MN, B_MN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p);
+  }
   if (g_profile) {
     cudaEventRecord(e1, stream);
     g_profile_events.emplace_back(e0, e1);
@@ -632,10 +682,32 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
       return launch_gemm_persistent(tmA, tmB, tmO, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }
 
-  if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, tmO, p, grid, smem, stream);
-  if (!a_mn && b_mn) return launch_impl<false, true>(tmA, tmB, tmO, p, grid, smem, stream);
-  if (a_mn && b_mn) return launch_impl<true, true>(tmA, tmB, tmO, p, grid, smem, stream);
-  return launch_impl<true, false>(tmA, tmB, tmO, p, grid, smem, stream);
+  // ---- B multicast over a cluster of CTAs that share the n tile (adjacent m tiles)
+  static const int cluster_env = getenv("MDM_GEMM_CLUSTER") ? atoi(getenv("MDM_GEMM_CLUSTER")) : 2;
+  alignas(64) CUtensorMap tmBpart = tmB;
+  p.cluster = 1;
+  {
+    int cs = cluster_env;
+    if (cs != 2 && cs != 4) cs = 1;
+    const int nslab = nb_alloc / 64;
+    while (cs > 1 && !(m_tiles >= 2 * cs && p.block_n >= 128 &&
+                       (b_mn ? (nslab % cs == 0) : ((p.block_n / cs) % 8 == 0))))
+      cs >>= 1;
+    if (cs > 1 && !b_mn) {  // K-major B: each CTA fetches block_n / cs rows of the tile
+      TmapSpec part = B;
+      part.box[1] = static_cast<uint32_t>(p.block_n / cs);
+      if (encode_tmap(&tmBpart, part) != 0) cs = 1;
+    }
+    if (cs > 1) {
+      p.cluster = cs;
+      grid.x = static_cast<unsigned>((m_tiles + cs - 1) / cs * cs);
+    }
+  }
+
+  if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  if (!a_mn && b_mn) return launch_impl<false, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  if (a_mn && b_mn) return launch_impl<true, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  return launch_impl<true, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
 }
 
 }  // namespace mdm

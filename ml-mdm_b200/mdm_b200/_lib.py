@@ -63,6 +63,7 @@ class GemmParams(C.Structure):
         ("atomic", C.c_int32),
         ("epi_tma", C.c_int32),
         ("gelu_grad_src", C.c_void_p),
+        ("cluster", C.c_int32),
         ("kfactor", C.c_int32),
     ]
 

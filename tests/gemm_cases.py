@@ -217,6 +217,18 @@ CASES = [
     ("conv_dgrad_mix", lambda: run_conv_dgrad(1, 32, 32, 64, 192, 64)),
     ("conv_wgrad_16", lambda: run_conv_wgrad(2, 16, 16, 128, 128, 128)),
     ("conv_wgrad_split", lambda: run_conv_wgrad(4, 32, 32, 64, 256, 64, nsplit=4)),
+    # >= 4 m tiles and >= 128 columns: clusters of 2 CTAs share the B tile by TMA multicast (MDM_GEMM_CLUSTER)
+    ("mc_kk_1024", lambda: run_plain(1024, 256, 512, 0, 0, 256, bias=True)),
+    ("mc_kk_ragged_m", lambda: run_plain(640 + 37, 384, 256, 0, 0, 128, bias=True, residual=True, f16_out=True)),
+    ("mc_kmn_1024", lambda: run_plain(1024, 256, 512, 0, 1, 256)),
+    ("mc_kmn_bn128", lambda: run_plain(768, 128, 320, 0, 1, 128)),
+    ("mc_mnmn_split", lambda: run_plain(1024, 256, 2048, 1, 1, 256, nsplit=4)),
+    ("mc_kk_batched", lambda: run_plain(512, 256, 128, 0, 0, 256, nz1=3, nz2=2)),
+    ("mc_conv_fwd", lambda: run_conv_fwd(4, 32, 32, 128, 256, 256)),
+    ("mc_conv_fwd_odd_tiles", lambda: run_conv_fwd(3, 24, 40, 64, 128, 128)),
+    ("mc_conv_dgrad", lambda: run_conv_dgrad(4, 32, 32, 256, 128, 256)),
+    ("mc_conv_dgrad_bn128", lambda: run_conv_dgrad(2, 32, 32, 128, 192, 128)),
+    ("mc_conv_wgrad", lambda: run_conv_wgrad(4, 32, 32, 256, 512, 256, nsplit=4)),
     # narrow layers (the 32/64-channel levels of the 256/1024-px nests): 256-pixel stages, one A slab when M <= 64
     ("conv_wgrad_tall_c32", lambda: run_conv_wgrad(2, 64, 64, 32, 32, 32, nsplit=4, kfactor=4)),
     ("conv_wgrad_tall_c64", lambda: run_conv_wgrad(3, 32, 48, 64, 64, 64, nsplit=3, kfactor=4)),
