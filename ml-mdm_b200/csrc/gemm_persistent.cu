@@ -38,8 +38,8 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
-                          const __grid_constant__ CUtensorMap tmOact, const GemmParams p, int m_tiles, int n_tiles,
-                          int num_tiles, int staging_bytes) {
+                          const __grid_constant__ CUtensorMap tmOact, const __grid_constant__ CUtensorMap tmBpart,
+                          const GemmParams p, int m_tiles, int n_tiles, int num_tiles, int staging_bytes) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -57,13 +57,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
   const int nstages = p.num_stages;
   const int nkb = p.num_kblocks;
+  // Cluster of cs CTAs: consecutive CTAs walk consecutive m tiles of the same n tile (m_tiles is padded to a multiple
+  // of cs by the launcher), so they share the B tile: each fetches 1/cs of it and multicasts (see gemm_tc.cu).
+  const int cs = p.cluster > 1 ? p.cluster : 1;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(cs));
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -74,6 +79,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -119,7 +125,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
               tma_load_4d(sA, &tmA, bar, m0, kb * BLOCK_K, az1, az2);
               tma_load_4d(sA + SLAB_BYTES, &tmA, bar, m0 + 64, kb * BLOCK_K, az1, az2);
             }
-            if (!B_MN) {
+            if (cs > 1) {
+              if (!B_MN) {
+                const int rows = p.block_n / cs;
+                tma_load_4d_mc(sB + crank * rows * 128, &tmBpart, bar, kb * BLOCK_K, n0 + crank * rows, bz1, bz2, cmask);
+              } else {
+                for (int s = crank; s < nslab_b; s += cs)
+                  tma_load_4d_mc(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, kb * BLOCK_K, bz1, bz2, cmask);
+              }
+            } else if (!B_MN) {
               tma_load_4d(sB, &tmB, bar, kb * BLOCK_K, n0, bz1, bz2);
             } else {
               for (int s = 0; s < nslab_b; ++s)
@@ -131,10 +145,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const int kh = (p.taps == 9) ? tap / 3 : 1;
             const int kw = (p.taps == 9) ? tap % 3 : 1;
             tma_load_4d(sA, &tmA, bar, cb * BLOCK_K, tw * p.PW + kw - 1, th * p.PH + kh - 1, img);
-            if (!B_MN) {
+            const int wt = p.flip ? (p.taps - 1 - tap) : tap;
+            if (cs > 1) {
+              if (!B_MN) {
+                const int rows = p.block_n / cs;
+                tma_load_4d_mc(sB + crank * rows * 128, &tmBpart, bar, cb * BLOCK_K, n0 + crank * rows, tap, 0, cmask);
+              } else {
+                for (int s = crank; s < nslab_b; s += cs)
+                  tma_load_4d_mc(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, cb * BLOCK_K, wt, 0, cmask);
+              }
+            } else if (!B_MN) {
               tma_load_4d(sB, &tmB, bar, cb * BLOCK_K, n0, tap, 0);
             } else {
-              const int wt = p.flip ? (p.taps - 1 - tap) : tap;
               for (int s = 0; s < nslab_b; ++s)
                 tma_load_4d(sB + s * SLAB_BYTES, &tmB, bar, n0 + 64 * s, cb * BLOCK_K, wt, 0);
             }
@@ -172,7 +194,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                                         : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
             umma_f16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -211,7 +234,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         img = t / p.tiles_h;
         const int ph = r / p.PW, pw = r - ph * p.PW;
         const int h = th * p.PH + ph, w = tw * p.PW + pw;
-        valid = (h < p.H) && (w < p.W);
+        valid = (h < p.H) && (w < p.W) && (img < p.nimg);  // (m_tiles is padded to whole clusters)
         row_off = (static_cast<long long>(img * p.H + h) * p.W + w) * p.ldc;
         oc1 = tw * p.PW; oc2 = th * p.PH; oc3 = img;
       } else {
@@ -377,12 +400,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 template <bool A_MN, bool B_MN>
-int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const GemmParams& p, int m_tiles,
-             int n_tiles, int num_tiles, int grid, size_t smem, int staging_bytes, cudaStream_t stream) {
+int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap& tmBpart,
+             const GemmParams& p, int m_tiles, int n_tiles, int num_tiles, int grid, size_t smem, int staging_bytes,
+             cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<A_MN, B_MN>,
@@ -396,8 +421,26 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* 
     cudaEventCreate(&e1);
     cudaEventRecord(e0, stream);
   }
-  gemm_tc_persistent_kernel<A_MN, B_MN><<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], p, m_tiles,
-                                                                         n_tiles, num_tiles, staging_bytes);
+  if (p.cluster > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_persistent_kernel<A_MN, B_MN>, tmA, tmB, tmO[0], tmO[1], tmO[2],
+                                        tmBpart, p, m_tiles, n_tiles, num_tiles, staging_bytes);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  } else {
+    gemm_tc_persistent_kernel<A_MN, B_MN><<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p,
+                                                                           m_tiles, n_tiles, num_tiles, staging_bytes);
+  }
   if (g_profile) {
     cudaEventRecord(e1, stream);
     g_profile_events.emplace_back(e0, e1);
@@ -411,8 +454,9 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* 
 }  // namespace
 
 // Called by launch_gemm when the launch is eligible (no split-K, TMA-store epilogue, not wgrad).
-int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, int a_mn, int b_mn,
-                           GemmParams p, int m_tiles, int n_tiles, cudaStream_t stream) {
+int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO,
+                           const CUtensorMap& tmBpart, int cluster, int a_mn, int b_mn, GemmParams p, int m_tiles,
+                           int n_tiles, cudaStream_t stream) {
   const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
   const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
   const int staging = (p.out_f32 ? 32768 : 0) + (p.out_f16 ? 16384 : 0) + (p.out_act_f16 ? 16384 : 0);
@@ -421,15 +465,20 @@ int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   if (stages < 2) return -30;
   p.num_stages = stages;
   const size_t smem = static_cast<size_t>(staging) + static_cast<size_t>(stages) * stage_bytes + 1024;
+  p.cluster = cluster > 1 ? cluster : 1;
+  if (p.cluster > 1) m_tiles = (m_tiles + p.cluster - 1) / p.cluster * p.cluster;  // ghost tiles store nothing
   const int num_tiles = m_tiles * n_tiles * p.nz1 * p.nz2;
   // g_sm_reserve SMs are left to a concurrently running collective (mdm_set_sm_reserve): with a static tile stride a
   // CTA that cannot become resident would otherwise serialise its whole share of tiles behind the others
-  const int sms = 148 - g_sm_reserve;
-  const int grid = num_tiles < sms ? num_tiles : sms;
-  if (!a_mn && !b_mn) return launch_p<false, false>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
-  if (!a_mn && b_mn) return launch_p<false, true>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
-  if (a_mn && b_mn) return launch_p<true, true>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
-  return launch_p<true, false>(tmA, tmB, tmO, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  const int sms = (148 - g_sm_reserve) / p.cluster * p.cluster;
+  const int grid = num_tiles < sms ? num_tiles : sms;  // (num_tiles is a multiple of the cluster size)
+  if (!a_mn && !b_mn)
+    return launch_p<false, false>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  if (!a_mn && b_mn)
+    return launch_p<false, true>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  if (a_mn && b_mn)
+    return launch_p<true, true>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  return launch_p<true, false>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
 }
 
 }  // namespace mdm

@@ -669,25 +669,15 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
     }
   }
 
-  // persistent warp-specialised variant (gemm_persistent.cu) for the non-split, TMA-store launches
-  static const bool persistent = getenv("MDM_GEMM_NO_PERSISTENT") == nullptr;
-  // Measured (B200): the persistent kernel wins where the epilogue matters (K <= ~3000: 16384x3072x768 runs at
-  // 1048 vs 824 TFLOP/s) and loses on long-K tiles, where two co-resident CTAs hide latency better
-  // (8192^3: 1196 vs 1353), and when the tile count leaves a mostly empty last round.
-  {
-    const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
-    const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
-    static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 96;
-    if (persistent && p.block_n >= persist_min_n && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
-      return launch_gemm_persistent(tmA, tmB, tmO, a_mn, b_mn, p, m_tiles, n_tiles, stream);
-  }
-
   // ---- B multicast over a cluster of CTAs that share the n tile (adjacent m tiles)
-  static const int cluster_env = getenv("MDM_GEMM_CLUSTER") ? atoi(getenv("MDM_GEMM_CLUSTER")) : 2;
+  // Off by default: measured (profiles/r02_multicast.txt) it changes nothing or costs 3-5 % -- the multicast removes
+  // L2 -> SM requests, but every SM still writes the whole B tile into its shared memory, and shared-memory traffic
+  // (TMA writes + tcgen05 operand reads, ~190 B/clk against 128 B/clk for a 128 x 256 tile) is what holds the
+  // one-CTA MMA at ~1.1 PFLOP/s; only cta_group::2 (half of B per SM) removes that.
+  static const int cluster_env = getenv("MDM_GEMM_CLUSTER") ? atoi(getenv("MDM_GEMM_CLUSTER")) : 1;
   alignas(64) CUtensorMap tmBpart = tmB;
-  p.cluster = 1;
+  int cs = cluster_env;
   {
-    int cs = cluster_env;
     if (cs != 2 && cs != 4) cs = 1;
     const int nslab = nb_alloc / 64;
     while (cs > 1 && !(m_tiles >= 2 * cs && p.block_n >= 128 &&
@@ -698,12 +688,26 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
       part.box[1] = static_cast<uint32_t>(p.block_n / cs);
       if (encode_tmap(&tmBpart, part) != 0) cs = 1;
     }
-    if (cs > 1) {
-      p.cluster = cs;
-      grid.x = static_cast<unsigned>((m_tiles + cs - 1) / cs * cs);
-    }
+  }
+  p.cluster = 1;
+
+  // persistent warp-specialised variant (gemm_persistent.cu) for the non-split, TMA-store launches
+  static const bool persistent = getenv("MDM_GEMM_NO_PERSISTENT") == nullptr;
+  // Measured (B200): the persistent kernel wins where the epilogue matters (K <= ~3000: 16384x3072x768 runs at
+  // 1048 vs 824 TFLOP/s) and loses on long-K tiles, where two co-resident CTAs hide latency better
+  // (8192^3: 1196 vs 1353), and when the tile count leaves a mostly empty last round.
+  {
+    const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
+    const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
+    static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 96;
+    if (persistent && p.block_n >= persist_min_n && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
+      return launch_gemm_persistent(tmA, tmB, tmO, tmBpart, cs, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }
 
+  if (cs > 1) {
+    p.cluster = cs;
+    grid.x = static_cast<unsigned>((m_tiles + cs - 1) / cs * cs);
+  }
   if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
   if (!a_mn && b_mn) return launch_impl<false, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
   if (a_mn && b_mn) return launch_impl<true, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
