@@ -113,7 +113,7 @@ def run_case(kind, batch=2, tokens=6, dtype=torch.float64, verbose=True, res=Non
         bad_a = {k: v for k, v in acts.items() if isinstance(v, str) or v > 2e-3}
         print(f"   activations checked: {len(acts)}, above 2e-3: {bad_a}")
         worst = sorted(grads.items(), key=lambda kv: -(kv[1] if kv[1] == kv[1] else 1e9))[:12]
-        print("   worst grads:", [(k, f"{v:.2e}") for k, v in worst])
+        print("   worst grads (ours, reference-tf32):", [(k, f"{v:.2e}", f"{report['tf32_grads'][k]:.2e}") for k, v in worst])
         print(f"   grads above 5e-3: {sum(1 for v in grads.values() if not (v <= 5e-3))} / {len(grads)}")
         print("   pool bytes (reserved, high-water):", model.native().workspace_bytes())
     return report
