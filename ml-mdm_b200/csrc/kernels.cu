@@ -6,6 +6,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "gemm_tc.cuh"  // g_launch_count
 
@@ -140,6 +142,97 @@ inline int pixel_chunks(int N, int HW, int ppi_hint, int per_sm = 8) {
 inline int host_ppi(int C) {
   int lanes = C / 4;
   return lanes <= TPB ? TPB / lanes : 1;
+}
+
+
+// ------------------------------------------------------------------ bulk-copy staged streaming
+// The GroupNorm backward kernels were latency-bound (ncu: 34 % occupancy at ~80 registers, 59 % of the warp cycles
+// waiting on global loads, 3.0 TB/s): the loads in flight lived in registers. Here one thread feeds a ring of
+// shared-memory stages with cp.async.bulk (the TMA engine, 1-D), so the bytes in flight no longer cost registers:
+// every CTA keeps STAGES x ~24-36 KB outstanding, the 256 threads read their float4 lanes from shared memory.
+constexpr int RS_STAGES = 3;
+
+__device__ __forceinline__ uint32_t rs_smem(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void rs_bar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rs_smem(bar)));
+}
+__device__ __forceinline__ void rs_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   rs_smem(dst)),
+               "l"(src), "r"(bytes), "r"(rs_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void rs_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(rs_smem(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();  // a protocol bug must not hang the GPU box
+  }
+}
+
+// Stage layout: [x source 0: pix * c0 fp32][x source 1: pix * c1 fp32][dy: pix * C (fp16 | fp32)]
+struct RowStage {
+  const float* x0;
+  const float* x1;
+  const uint8_t* dy;
+};
+struct RowStream {
+  uint8_t* base;
+  uint64_t* full;  // [RS_STAGES]
+  int stage_bytes, x0_bytes_pp, x1_bytes_pp, dy_bytes_pp, pix;  // bytes per pixel of each part, pixels per chunk
+  __device__ __forceinline__ RowStage stage(int s) const {
+    uint8_t* b = base + static_cast<size_t>(s) * stage_bytes;
+    RowStage r;
+    r.x0 = reinterpret_cast<const float*>(b);
+    r.x1 = reinterpret_cast<const float*>(b + static_cast<size_t>(pix) * x0_bytes_pp);
+    r.dy = b + static_cast<size_t>(pix) * (x0_bytes_pp + x1_bytes_pp);
+    return r;
+  }
+  // one thread: fetch pixels [pix0, pix0 + np) of sample-major tensors into stage s
+  __device__ __forceinline__ void issue(int s, const Src2& x, const void* dy, long long pix0, int np) const {
+    uint8_t* b = base + static_cast<size_t>(s) * stage_bytes;
+    const uint32_t b0 = static_cast<uint32_t>(np) * x0_bytes_pp, b1 = static_cast<uint32_t>(np) * x1_bytes_pp,
+                   b2 = static_cast<uint32_t>(np) * dy_bytes_pp;
+    rs_expect(&full[s], b0 + b1 + b2);
+    rs_copy(b, reinterpret_cast<const uint8_t*>(x.p0) + pix0 * x0_bytes_pp, b0, &full[s]);
+    if (b1 > 0)
+      rs_copy(b + static_cast<size_t>(pix) * x0_bytes_pp, reinterpret_cast<const uint8_t*>(x.p1) + pix0 * x1_bytes_pp, b1,
+              &full[s]);
+    if (b2 > 0)
+      rs_copy(b + static_cast<size_t>(pix) * (x0_bytes_pp + x1_bytes_pp), static_cast<const uint8_t*>(dy) + pix0 * dy_bytes_pp,
+              b2, &full[s]);
+  }
+};
+__device__ __forceinline__ float4 rs_ld_x(const RowStage& st, const Src2& x, int pl, int c) {
+  if (c < x.c0) return *reinterpret_cast<const float4*>(st.x0 + static_cast<size_t>(pl) * x.c0 + c);
+  return *reinterpret_cast<const float4*>(st.x1 + static_cast<size_t>(pl) * x.c1 + (c - x.c0));
+}
+template <bool F16>
+__device__ __forceinline__ float4 rs_ld_dy(const RowStage& st, int C, int pl, int c) {
+  if (F16) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(st.dy + (static_cast<size_t>(pl) * C + c) * 2);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(st.dy + (static_cast<size_t>(pl) * C + c) * 4);
+}
+// host: pixels per chunk (a multiple of the CTA's pixels-per-pass) for ~16 KB of x per stage, and the stage size
+inline void rs_geometry(int C, int dy_esz, int* pix, int* stage_bytes) {
+  const int ppi = host_ppi(C);
+  int px = std::max(1, 16384 / (C * 4));
+  px = std::max(ppi, px / ppi * ppi);
+  *pix = px;
+  *stage_bytes = (px * C * (4 + dy_esz) + 127) / 128 * 128;
 }
 
 // ------------------------------------------------------------------ GroupNorm statistics
@@ -386,6 +479,89 @@ gn_bwd_reduce_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const f
   }
 }
 
+
+template <int NL, bool DY16>
+__global__ void __launch_bounds__(TPB)
+gn_bwd_reduce_staged_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ film, int film_ld, int film_off, int silu,
+                            float* __restrict__ ab, int pix, int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t rs_mem[];
+  __shared__ __align__(8) uint64_t full[RS_STAGES];
+  __shared__ float4 red[TPB];
+  const int C = x.c0 + x.c1;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(cdiv(HW, gridDim.x), pix)) * pix;  // whole chunks per CTA
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  const int nchunks = p_end > p_begin ? static_cast<int>(cdiv(p_end - p_begin, pix)) : 0;
+  RowStream rs{rs_mem, full, stage_bytes, x.c0 * 4, x.c1 * 4, C * (DY16 ? 2 : 4), pix};
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RS_STAGES; ++s) rs_bar_init(&full[s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long base_pix = static_cast<long long>(n) * HW;
+  if (threadIdx.x == 0)
+    for (int it = 0; it < RS_STAGES && it < nchunks; ++it)
+      rs.issue(it, x, dy, base_pix + p_begin + it * pix, min(pix, p_end - p_begin - it * pix));
+  GnCoef<NL> k;
+  if (m.active) gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  float4 A[NL], Bq[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    A[j] = make_float4(0, 0, 0, 0);
+    Bq[j] = make_float4(0, 0, 0, 0);
+  }
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % RS_STAGES;
+    rs_wait(&full[s], static_cast<uint32_t>(it / RS_STAGES) & 1u);
+    const RowStage st = rs.stage(s);
+    const int np = min(pix, p_end - p_begin - it * pix);
+    if (m.active) {
+      for (int pl = m.sub; pl < np; pl += m.ppi) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          const int l = m.t_lane + j * m.stride;
+          if (l < m.lanes) {
+            const float4 v = rs_ld_x(st, x, pl, 4 * l);
+            const float4 d = rs_ld_dy<DY16>(st, C, pl, 4 * l);
+            const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
+                                 v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
+            const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
+            const float be[4] = {k.be[j].x, k.be[j].y, k.be[j].z, k.be[j].w};
+            float du[4] = {d.x, d.y, d.z, d.w};
+            if (silu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) du[e] *= silu_grad(xh[e] * ga[e] + be[e]);
+            }
+            A[j].x += du[0]; A[j].y += du[1]; A[j].z += du[2]; A[j].w += du[3];
+            Bq[j].x += du[0] * xh[0]; Bq[j].y += du[1] * xh[1]; Bq[j].z += du[2] * xh[2]; Bq[j].w += du[3] * xh[3];
+          }
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (threadIdx.x == 0 && it + RS_STAGES < nchunks)
+      rs.issue(s, x, dy, base_pix + p_begin + (it + RS_STAGES) * pix, min(pix, p_end - p_begin - (it + RS_STAGES) * pix));
+  }
+  reduce_over_subs(A, m, red);
+  reduce_over_subs(Bq, m, red);
+  if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int l = m.t_lane + j * m.stride;
+    if (l < m.lanes) {
+      float* o = ab + (static_cast<long long>(n) * C + 4 * l) * 2;
+      atomicAdd(o + 0, A[j].x); atomicAdd(o + 1, Bq[j].x);
+      atomicAdd(o + 2, A[j].y); atomicAdd(o + 3, Bq[j].y);
+      atomicAdd(o + 4, A[j].z); atomicAdd(o + 5, Bq[j].z);
+      atomicAdd(o + 6, A[j].w); atomicAdd(o + 7, Bq[j].w);
+    }
+  }
+}
+
 __global__ void gn_bwd_finalize_kernel(int C, int G, int HW, const float* __restrict__ ab,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        const float* __restrict__ film, int film_ld, int film_off,
@@ -533,6 +709,133 @@ gn_bwd_apply_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const fl
     }
   }
   if (dst.h16 != nullptr && dst.colsum != nullptr) {  // kernel-argument condition: uniform over the block
+    reduce_over_subs(csum, m, red);
+    if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
+    const float inv = dst.inv_scale != nullptr ? __ldg(dst.inv_scale) : 1.f;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = m.t_lane + j * m.stride;
+      if (l < m.lanes) {
+        atomicAdd(dst.colsum + 4 * l + 0, inv * csum[j].x);
+        atomicAdd(dst.colsum + 4 * l + 1, inv * csum[j].y);
+        atomicAdd(dst.colsum + 4 * l + 2, inv * csum[j].z);
+        atomicAdd(dst.colsum + 4 * l + 3, inv * csum[j].w);
+      }
+    }
+  }
+}
+
+
+template <int NL, bool DY16>
+__global__ void __launch_bounds__(TPB)
+gn_bwd_apply_staged_kernel(Src2 x, const void* __restrict__ dy, int HW, int G, const float* __restrict__ sums,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ film, int film_ld, int film_off, int silu,
+                           const float* __restrict__ pg, const float* __restrict__ extra, Dst2 dst, int pix,
+                           int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t rs_mem[];
+  __shared__ __align__(8) uint64_t full[RS_STAGES];
+  __shared__ float4 red[TPB];
+  const int C = x.c0 + x.c1;
+  const int cpg = C / G;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(cdiv(HW, gridDim.x), pix)) * pix;
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  const int nchunks = p_end > p_begin ? static_cast<int>(cdiv(p_end - p_begin, pix)) : 0;
+  RowStream rs{rs_mem, full, stage_bytes, x.c0 * 4, x.c1 * 4, C * (DY16 ? 2 : 4), pix};
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RS_STAGES; ++s) rs_bar_init(&full[s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long base_pix = static_cast<long long>(n) * HW;
+  if (threadIdx.x == 0)
+    for (int it = 0; it < RS_STAGES && it < nchunks; ++it)
+      rs.issue(it, x, dy, base_pix + p_begin + it * pix, min(pix, p_end - p_begin - it * pix));
+  GnCoef<NL> k;
+  if (m.active) gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  float4 csum[NL], q1[NL], q2[NL];
+  const float inv_m = 1.0f / (static_cast<float>(HW) * cpg);
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    csum[j] = make_float4(0, 0, 0, 0);
+    const int l = m.t_lane + j * m.stride;
+    if (m.active && l < m.lanes) {
+      float a[4], b[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int g = (4 * l + e) / cpg;
+        a[e] = __ldg(pg + (static_cast<long long>(n) * G + g) * 2) * inv_m;
+        b[e] = __ldg(pg + (static_cast<long long>(n) * G + g) * 2 + 1) * inv_m;
+      }
+      q1[j] = make_float4(a[0], a[1], a[2], a[3]);
+      q2[j] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+  }
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % RS_STAGES;
+    rs_wait(&full[s], static_cast<uint32_t>(it / RS_STAGES) & 1u);
+    const RowStage st = rs.stage(s);
+    const int np = min(pix, p_end - p_begin - it * pix);
+    if (m.active) {
+      for (int pl = m.sub; pl < np; pl += m.ppi) {
+        const long long gpix = base_pix + p_begin + it * pix + pl;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          const int l = m.t_lane + j * m.stride;
+          if (l < m.lanes) {
+            const int c = 4 * l;
+            const float4 v = rs_ld_x(st, x, pl, c);
+            const float4 d = rs_ld_dy<DY16>(st, C, pl, c);
+            const float xh[4] = {v.x * k.rs[j].x + k.nm[j].x, v.y * k.rs[j].y + k.nm[j].y,
+                                 v.z * k.rs[j].z + k.nm[j].z, v.w * k.rs[j].w + k.nm[j].w};
+            const float ga[4] = {k.ga[j].x, k.ga[j].y, k.ga[j].z, k.ga[j].w};
+            const float be[4] = {k.be[j].x, k.be[j].y, k.be[j].z, k.be[j].w};
+            const float rsd[4] = {k.rs[j].x, k.rs[j].y, k.rs[j].z, k.rs[j].w};
+            const float a1[4] = {q1[j].x, q1[j].y, q1[j].z, q1[j].w};
+            const float a2[4] = {q2[j].x, q2[j].y, q2[j].z, q2[j].w};
+            float du[4] = {d.x, d.y, d.z, d.w};
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (silu) du[e] *= silu_grad(xh[e] * ga[e] + be[e]);
+              r[e] = rsd[e] * (du[e] * ga[e] - a1[e] - xh[e] * a2[e]);
+            }
+            if (extra != nullptr) {
+              const float4 ex = __ldg(reinterpret_cast<const float4*>(extra + gpix * C + c));
+              r[0] += ex.x; r[1] += ex.y; r[2] += ex.z; r[3] += ex.w;
+            }
+            if (dst.h16 != nullptr) {
+              st_half4(dst.h16 + gpix * C + c, r[0], r[1], r[2], r[3]);
+              csum[j].x += r[0]; csum[j].y += r[1]; csum[j].z += r[2]; csum[j].w += r[3];
+              continue;
+            }
+            float* o;
+            int acc;
+            if (c < dst.c0) {
+              o = dst.p0 + gpix * dst.c0 + c;
+              acc = dst.acc0;
+            } else {
+              o = dst.p1 + gpix * dst.c1 + (c - dst.c0);
+              acc = dst.acc1;
+            }
+            float4 outv = make_float4(r[0], r[1], r[2], r[3]);
+            if (acc) {
+              const float4 old = *reinterpret_cast<const float4*>(o);
+              outv.x += old.x; outv.y += old.y; outv.z += old.z; outv.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o) = outv;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + RS_STAGES < nchunks)
+      rs.issue(s, x, dy, base_pix + p_begin + (it + RS_STAGES) * pix, min(pix, p_end - p_begin - (it + RS_STAGES) * pix));
+  }
+  if (dst.h16 != nullptr && dst.colsum != nullptr) {
     reduce_over_subs(csum, m, red);
     if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
     const float inv = dst.inv_scale != nullptr ? __ldg(dst.inv_scale) : 1.f;
@@ -1241,10 +1544,47 @@ void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const floa
                                                                 y16, raw16)));
   MDM_LAUNCHED();
 }
+// staged (bulk-copy ring) forms of the GroupNorm backward kernels; MDM_GN_LEGACY=1 selects the register-fed ones
+static const bool g_gn_staged = getenv("MDM_GN_LEGACY") == nullptr;
+template <typename K>
+static void rs_set_smem(K kernel, int bytes) {
+  static std::vector<std::pair<const void*, int>> done;  // (kernel, largest size allowed so far)
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (auto& d : done)
+    if (d.first == key) {
+      if (bytes > d.second) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        d.second = bytes;
+      }
+      return;
+    }
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done.emplace_back(key, bytes);
+}
+#define MDM_LAUNCH_STAGED(KERNEL, grid, smem, ...)        \
+  do {                                                    \
+    rs_set_smem(KERNEL, smem);                            \
+    KERNEL<<<grid, TPB, smem, st>>>(__VA_ARGS__);         \
+  } while (0)
+
 void gn_bwd_reduce(const Src2& x, const void* dy, int dy_f16, int N, int HW, int G, const float* sums,
                    const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
                    float* ab, cudaStream_t st) {
   const int C = x.c0 + x.c1;
+  if (g_gn_staged && (x.c0 % 4 == 0) && (x.c1 % 4 == 0) && (C % 8 == 0)) {
+    int pix, sb;
+    rs_geometry(C, dy_f16 ? 2 : 4, &pix, &sb);
+    const int smem = RS_STAGES * sb;
+    dim3 grid(pixel_chunks(N, HW, pix, 4), N);  // ~2 resident CTAs per SM, each with RS_STAGES chunks in flight
+    if (dy_f16)
+      MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_bwd_reduce_staged_kernel<NL, true>), grid, smem, x, dy, HW, G, sums, gamma, beta,
+                                           film, film_ld, film_off, silu, ab, pix, sb));
+    else
+      MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_bwd_reduce_staged_kernel<NL, false>), grid, smem, x, dy, HW, G, sums, gamma,
+                                           beta, film, film_ld, film_off, silu, ab, pix, sb));
+    MDM_LAUNCHED();
+    return;
+  }
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
   if (dy_f16)
     MDM_DISPATCH_NL(C, (gn_bwd_reduce_kernel<NL, true><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
@@ -1265,6 +1605,20 @@ void gn_bwd_apply(const Src2& x, const void* dy, int dy_f16, int N, int HW, int 
                   const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
                   const float* pg, const float* extra, const Dst2& dst, cudaStream_t st) {
   const int C = x.c0 + x.c1;
+  if (g_gn_staged && (x.c0 % 4 == 0) && (x.c1 % 4 == 0) && (C % 8 == 0)) {
+    int pix, sb;
+    rs_geometry(C, dy_f16 ? 2 : 4, &pix, &sb);
+    const int smem = RS_STAGES * sb;
+    dim3 grid(pixel_chunks(N, HW, pix, 4), N);
+    if (dy_f16)
+      MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_bwd_apply_staged_kernel<NL, true>), grid, smem, x, dy, HW, G, sums, gamma, beta,
+                                           film, film_ld, film_off, silu, pg, extra, dst, pix, sb));
+    else
+      MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_bwd_apply_staged_kernel<NL, false>), grid, smem, x, dy, HW, G, sums, gamma,
+                                           beta, film, film_ld, film_off, silu, pg, extra, dst, pix, sb));
+    MDM_LAUNCHED();
+    return;
+  }
   dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
   if (dy_f16)
     MDM_DISPATCH_NL(C, (gn_bwd_apply_kernel<NL, true><<<grid, TPB, 0, st>>>(x, dy, HW, G, sums, gamma, beta, film, film_ld,
