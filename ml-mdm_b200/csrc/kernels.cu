@@ -908,6 +908,123 @@ cast_colsum_kernel(const void* __restrict__ in_, __half* __restrict__ out16, lon
   atomicAdd(colsum + c + 3, inv * s.w);
 }
 
+
+// staged fp32 -> fp16 cast + column sums (single channel tile: C <= 4 * TPB)
+__global__ void __launch_bounds__(TPB)
+cast_colsum_staged_kernel(const float* __restrict__ in, __half* __restrict__ out16, long long rows, int C,
+                          float* __restrict__ colsum, const float* __restrict__ inv_scale, int pix, int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t rs_mem[];
+  __shared__ __align__(8) uint64_t full[RS_STAGES];
+  __shared__ float4 red[TPB];
+  const LaneMap m = lane_map(C);
+  const long long per = cdiv(cdiv(rows, static_cast<long long>(gridDim.x)), pix) * pix;
+  const long long r_begin = blockIdx.x * per;
+  const long long r_end = min(rows, r_begin + per);
+  const int nchunks = r_end > r_begin ? static_cast<int>(cdiv(r_end - r_begin, pix)) : 0;
+  const Src2 x{in, nullptr, C, 0};
+  RowStream rs{rs_mem, full, stage_bytes, C * 4, 0, 0, pix};
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RS_STAGES; ++s) rs_bar_init(&full[s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int it = 0; it < RS_STAGES && it < nchunks; ++it)
+      rs.issue(it, x, nullptr, r_begin + static_cast<long long>(it) * pix,
+               static_cast<int>(min(static_cast<long long>(pix), r_end - r_begin - static_cast<long long>(it) * pix)));
+  float4 sacc = make_float4(0, 0, 0, 0);
+  const int c = 4 * m.t_lane;
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % RS_STAGES;
+    rs_wait(&full[s], static_cast<uint32_t>(it / RS_STAGES) & 1u);
+    const RowStage st = rs.stage(s);
+    const long long r0 = r_begin + static_cast<long long>(it) * pix;
+    const int np = static_cast<int>(min(static_cast<long long>(pix), r_end - r0));
+    if (m.active) {
+      for (int pl = m.sub; pl < np; pl += m.ppi) {
+        const float4 v = *reinterpret_cast<const float4*>(st.x0 + static_cast<size_t>(pl) * C + c);
+        if (out16 != nullptr) st_half4(out16 + (r0 + pl) * C + c, v.x, v.y, v.z, v.w);
+        sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + RS_STAGES < nchunks)
+      rs.issue(s, x, nullptr, r_begin + static_cast<long long>(it + RS_STAGES) * pix,
+               static_cast<int>(min(static_cast<long long>(pix), r_end - r_begin - static_cast<long long>(it + RS_STAGES) * pix)));
+  }
+  if (colsum == nullptr) return;
+  {
+    float4 sv[1] = {sacc};
+    reduce_over_subs(sv, m, red);
+    sacc = sv[0];
+  }
+  if (!m.active || (m.ppi > 1 && m.sub != 0)) return;
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.f;
+  atomicAdd(colsum + c + 0, inv * sacc.x);
+  atomicAdd(colsum + c + 1, inv * sacc.y);
+  atomicAdd(colsum + c + 2, inv * sacc.z);
+  atomicAdd(colsum + c + 3, inv * sacc.w);
+}
+
+// staged GroupNorm (+FiLM, +SiLU) apply
+template <int NL>
+__global__ void __launch_bounds__(TPB)
+gn_apply_staged_kernel(Src2 x, int HW, int G, const float* __restrict__ sums, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ film, int film_ld, int film_off,
+                       int silu, __half* __restrict__ y16, __half* __restrict__ raw16, int pix, int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t rs_mem[];
+  __shared__ __align__(8) uint64_t full[RS_STAGES];
+  const int C = x.c0 + x.c1;
+  const LaneMap m = lane_map(C);
+  const int n = blockIdx.y;
+  const int per = static_cast<int>(cdiv(cdiv(HW, gridDim.x), pix)) * pix;
+  const int p_begin = blockIdx.x * per;
+  const int p_end = min(HW, p_begin + per);
+  const int nchunks = p_end > p_begin ? static_cast<int>(cdiv(p_end - p_begin, pix)) : 0;
+  RowStream rs{rs_mem, full, stage_bytes, x.c0 * 4, x.c1 * 4, 0, pix};
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RS_STAGES; ++s) rs_bar_init(&full[s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long base_pix = static_cast<long long>(n) * HW;
+  if (threadIdx.x == 0)
+    for (int it = 0; it < RS_STAGES && it < nchunks; ++it)
+      rs.issue(it, x, nullptr, base_pix + p_begin + it * pix, min(pix, p_end - p_begin - it * pix));
+  GnCoef<NL> k;
+  if (m.active) gn_coefs(k, m, n, C, G, HW, sums, gamma, beta, film, film_ld, film_off);
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % RS_STAGES;
+    rs_wait(&full[s], static_cast<uint32_t>(it / RS_STAGES) & 1u);
+    const RowStage st = rs.stage(s);
+    const int np = min(pix, p_end - p_begin - it * pix);
+    if (m.active) {
+      for (int pl = m.sub; pl < np; pl += m.ppi) {
+        const long long gpix = base_pix + p_begin + it * pix + pl;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          const int l = m.t_lane + j * m.stride;
+          if (l < m.lanes) {
+            const float4 v = rs_ld_x(st, x, pl, 4 * l);
+            float u0 = (v.x * k.rs[j].x + k.nm[j].x) * k.ga[j].x + k.be[j].x;
+            float u1 = (v.y * k.rs[j].y + k.nm[j].y) * k.ga[j].y + k.be[j].y;
+            float u2 = (v.z * k.rs[j].z + k.nm[j].z) * k.ga[j].z + k.be[j].z;
+            float u3 = (v.w * k.rs[j].w + k.nm[j].w) * k.ga[j].w + k.be[j].w;
+            if (silu) {
+              u0 = siluf_(u0); u1 = siluf_(u1); u2 = siluf_(u2); u3 = siluf_(u3);
+            }
+            st_half4(y16 + gpix * C + 4 * l, u0, u1, u2, u3);
+            if (raw16 != nullptr) st_half4(raw16 + gpix * C + 4 * l, v.x, v.y, v.z, v.w);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + RS_STAGES < nchunks)
+      rs.issue(s, x, nullptr, base_pix + p_begin + (it + RS_STAGES) * pix, min(pix, p_end - p_begin - (it + RS_STAGES) * pix));
+  }
+}
+
 __global__ void cast_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
   long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
@@ -1529,22 +1646,7 @@ inline int grid_for(long long n, int tpb = 256, int cap = 148 * 16) {
 }  // namespace
 
 // ======================================================================== launchers
-void gn_stats(const Src2& x, int N, int HW, int G, float* sums, cudaStream_t st) {
-  const int C = x.c0 + x.c1;
-  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  MDM_DISPATCH_NL(C, (gn_stats_kernel<NL><<<grid, TPB, 0, st>>>(x, HW, G, sums)));
-  MDM_LAUNCHED();
-}
-void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const float* gamma, const float* beta,
-              const float* film, int film_ld, int film_off, int silu, __half* y16, __half* raw16,
-              cudaStream_t st) {
-  const int C = x.c0 + x.c1;
-  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
-  MDM_DISPATCH_NL(C, (gn_apply_kernel<NL><<<grid, TPB, 0, st>>>(x, HW, G, sums, gamma, beta, film, film_ld, film_off, silu,
-                                                                y16, raw16)));
-  MDM_LAUNCHED();
-}
-// staged (bulk-copy ring) forms of the GroupNorm backward kernels; MDM_GN_LEGACY=1 selects the register-fed ones
+// staged (bulk-copy ring) forms of the streaming kernels; MDM_GN_LEGACY=1 selects the register-fed ones
 static const bool g_gn_staged = getenv("MDM_GN_LEGACY") == nullptr;
 template <typename K>
 static void rs_set_smem(K kernel, int bytes) {
@@ -1561,12 +1663,48 @@ static void rs_set_smem(K kernel, int bytes) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   done.emplace_back(key, bytes);
 }
+// Grid of a staged kernel: every CTA resident at once (as many per SM as their shared memory allows, at most 4) and an
+// equal share of pixels each -- a partial second wave would leave most SMs idle for a whole CTA lifetime.
+static int staged_chunks(int N, int HW, int pix, int smem_bytes) {
+  int resident = std::min(4, std::max(1, (220 * 1024) / (smem_bytes + 6 * 1024)));
+  long long want = (static_cast<long long>(resident) * 148) / N;
+  const long long maxc = cdiv(HW, pix);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
 #define MDM_LAUNCH_STAGED(KERNEL, grid, smem, ...)        \
   do {                                                    \
     rs_set_smem(KERNEL, smem);                            \
     KERNEL<<<grid, TPB, smem, st>>>(__VA_ARGS__);         \
   } while (0)
 
+void gn_stats(const Src2& x, int N, int HW, int G, float* sums, cudaStream_t st) {
+  const int C = x.c0 + x.c1;
+  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
+  MDM_DISPATCH_NL(C, (gn_stats_kernel<NL><<<grid, TPB, 0, st>>>(x, HW, G, sums)));
+  MDM_LAUNCHED();
+}
+void gn_apply(const Src2& x, int N, int HW, int G, const float* sums, const float* gamma, const float* beta,
+              const float* film, int film_ld, int film_off, int silu, __half* y16, __half* raw16,
+              cudaStream_t st) {
+  const int C = x.c0 + x.c1;
+  static const bool staged_apply = getenv("MDM_APPLY_LEGACY") == nullptr;
+  if (g_gn_staged && staged_apply && (x.c0 % 4 == 0) && (x.c1 % 4 == 0) && (C % 8 == 0)) {
+    int pix, sb;
+    rs_geometry(C, 0, &pix, &sb);
+    const int smem = RS_STAGES * sb;
+    dim3 grid(staged_chunks(N, HW, pix, smem), N);
+    MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_apply_staged_kernel<NL>), grid, smem, x, HW, G, sums, gamma, beta, film, film_ld,
+                                         film_off, silu, y16, raw16, pix, sb));
+    MDM_LAUNCHED();
+    return;
+  }
+  dim3 grid(pixel_chunks(N, HW, host_ppi(C)), N);
+  MDM_DISPATCH_NL(C, (gn_apply_kernel<NL><<<grid, TPB, 0, st>>>(x, HW, G, sums, gamma, beta, film, film_ld, film_off, silu,
+                                                                y16, raw16)));
+  MDM_LAUNCHED();
+}
 void gn_bwd_reduce(const Src2& x, const void* dy, int dy_f16, int N, int HW, int G, const float* sums,
                    const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
                    float* ab, cudaStream_t st) {
@@ -1575,7 +1713,7 @@ void gn_bwd_reduce(const Src2& x, const void* dy, int dy_f16, int N, int HW, int
     int pix, sb;
     rs_geometry(C, dy_f16 ? 2 : 4, &pix, &sb);
     const int smem = RS_STAGES * sb;
-    dim3 grid(pixel_chunks(N, HW, pix, 4), N);  // ~2 resident CTAs per SM, each with RS_STAGES chunks in flight
+    dim3 grid(staged_chunks(N, HW, pix, smem), N);
     if (dy_f16)
       MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_bwd_reduce_staged_kernel<NL, true>), grid, smem, x, dy, HW, G, sums, gamma, beta,
                                            film, film_ld, film_off, silu, ab, pix, sb));
@@ -1609,7 +1747,7 @@ void gn_bwd_apply(const Src2& x, const void* dy, int dy_f16, int N, int HW, int 
     int pix, sb;
     rs_geometry(C, dy_f16 ? 2 : 4, &pix, &sb);
     const int smem = RS_STAGES * sb;
-    dim3 grid(pixel_chunks(N, HW, pix, 4), N);
+    dim3 grid(staged_chunks(N, HW, pix, smem), N);
     if (dy_f16)
       MDM_DISPATCH_NL(C, MDM_LAUNCH_STAGED((gn_bwd_apply_staged_kernel<NL, true>), grid, smem, x, dy, HW, G, sums, gamma, beta,
                                            film, film_ld, film_off, silu, pg, extra, dst, pix, sb));
@@ -1642,6 +1780,17 @@ static dim3 colsum_grid(long long rows, int C, bool coarse) {
 }
 void cast_colsum(const float* in, __half* out16, long long rows, int C, float* colsum, const float* inv_scale,
                  cudaStream_t st) {
+  static const bool staged_cast = getenv("MDM_CAST_LEGACY") == nullptr;
+  if (g_gn_staged && staged_cast && C <= 4 * TPB && C % 8 == 0 && rows >= 4096) {
+    int pix, sb;
+    rs_geometry(C, 0, &pix, &sb);
+    const int smem = RS_STAGES * sb;
+    const long long chunks = staged_chunks(1, static_cast<int>(std::min<long long>(rows, 2147483647ll)), pix, smem);
+    MDM_LAUNCH_STAGED(cast_colsum_staged_kernel, dim3(static_cast<unsigned>(chunks)), smem, in, out16, rows, C, colsum,
+                      inv_scale, pix, sb);
+    MDM_LAUNCHED();
+    return;
+  }
   cast_colsum_kernel<false><<<colsum_grid(rows, C, false), TPB, 0, st>>>(in, out16, rows, C, colsum, inv_scale);
   MDM_LAUNCHED();
 }

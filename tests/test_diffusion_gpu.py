@@ -27,6 +27,42 @@ def pipeline(kind):
     return pipe, oracle, sd, gold, x, lm, mask, nested
 
 
+def _calibrated_loss_check(pipe, oracle, sd, loss, P64, oloss, images, eps, time, lm, mask, scales, shifted, mixed_ratio=None):
+    """loss and every parameter gradient of get_loss against the fp64 oracle, bounded by what the reference's own GPU
+    arithmetic (the oracle in fp32 with TF32 on, same draws) scores on the same metric in the same run."""
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        P32 = {k: v.float().cuda().requires_grad_(True) for k, v in sd.items()}
+        gam = dref.gammas_f32("DEEPFLOYD", 1000).cuda()
+        tl, _, _ = dref.training_loss(oracle, P32, images.float().cuda(), [e.float().cuda() for e in eps], time.cuda(),
+                                      lm.float().cuda(), mask.float().cuda(), gam, scales, dref.V_PREDICTION, dref.DDPM,
+                                      shifted=shifted, power=1, mixed_ratio=mixed_ratio)
+        tl.mean().backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    ref_loss = oloss.detach()
+    e_ours = nc.rel(loss.detach().cpu().double(), ref_loss)
+    e_tf32 = nc.rel(tl.detach().cpu().double(), ref_loss)
+    assert e_ours <= max(2e-3, 2.5 * e_tf32), (e_ours, e_tf32)  # per-sample loss: a mean over CHW of squared errors
+    mags = sorted(float(P64[k].grad.abs().max()) for k in P64)
+    floor = 1e-2 * mags[len(mags) // 2]
+    ours, tf32 = {}, {}
+    for k, p in pipe.get_model().vision_model.named_parameters():
+        ref = P64[k].grad
+        den = max(float(ref.abs().max()), floor)
+        ours[k] = float((p.grad.cpu().double() - ref).abs().max() / den)
+        tf32[k] = float((P32[k].grad.cpu().double() - ref).abs().max() / den)
+    t = sorted(tf32.values())
+    o = sorted(ours.values())
+    med = t[len(t) // 2]
+    assert o[len(o) // 2] <= 1.5 * med, (o[len(o) // 2], med)
+    bad = {k: (v, tf32[k]) for k, v in ours.items() if not (v <= 3.5 * max(tf32[k], med))}
+    assert not bad, bad
+
+
 def test_q_sample_matches_to_one_ulp():
     """Not bit-exact by construction: torch's CPU sqrt kernel is not correctly rounded (differs from
     IEEE sqrt in ~0.6% of inputs), the device uses IEEE sqrt.rn; everything else is one rounding per op."""
@@ -64,16 +100,8 @@ def test_get_loss_and_gradients(kind):
                                         gam, scales, dref.V_PREDICTION, dref.DDPM, shifted=nested, power=1)
     assert nc.rel(x_t.cpu().double(), ox_t[0]) <= 1e-6
     oloss.mean().backward()
-    assert nc.rel(loss.detach().cpu().double(), oloss.detach()) <= 5e-3
-    mags = sorted(float(P[k].grad.abs().max()) for k in P)
-    floor = 1e-2 * mags[len(mags) // 2]
-    bad = {}
-    for k, p in pipe.get_model().vision_model.named_parameters():
-        ref = P[k].grad
-        e = float((p.grad.cpu().double() - ref).abs().max() / max(float(ref.abs().max()), floor))
-        if not e <= 3e-2:
-            bad[k] = e
-    assert not bad, bad
+    _calibrated_loss_check(pipe, oracle, sd, loss, P, oloss, images, [e.cpu() for e in eps], time.cpu(), lm, mask, scales,
+                           shifted=nested)
 
 
 @pytest.mark.parametrize("kind", ["unet", "nested"])
@@ -91,6 +119,7 @@ def test_reverse_steps_vs_reference_golden(kind):
         x0, xs, _ = smp.get_xt_minus_1(m, 500, clone(xc), lmc, mc_, {}, time_step_last=480, ddim_eta=0.0, return_details=True)
         for i, (a, b) in enumerate(zip(x0, xs) if nested else [(x0, xs)]):
             # one network evaluation (<= 2e-3 on v) pushed through x0 = a x_t - c v and the clip
+            # (single-evaluation bound 2.5e-3, amplified by 1/sqrt(gamma) ~ 1.4-2 in x0 = a x_t - c v)
             assert nc.rel(a.cpu(), torch.from_numpy(gold[f"ddim_x0_{i}"])) <= 5e-3
             assert nc.rel(b.cpu(), torch.from_numpy(gold[f"ddim_xs_{i}"])) <= 5e-3
         lm2 = torch.cat([torch.zeros_like(lmc), lmc])
@@ -128,7 +157,8 @@ def test_ddim_sampling_vs_reference_golden(kind):
     else:
         init = x.cuda()
     out = smp.sample(m, init, lm.cuda(), mask.cuda(), {}, num_inference_steps=4, ddim_eta=0.0, resample_steps=True)
-    assert nc.rel(out.cpu(), torch.from_numpy(gold["sample4"])) <= 1e-2  # 4 network evaluations compound
+    # four chained network evaluations, each within the single-evaluation bound of tests/test_net_gpu.py (2.5e-3)
+    assert nc.rel(out.cpu(), torch.from_numpy(gold["sample4"])) <= 4 * 2.5e-3
     assert float(out.abs().max()) <= 1.0
 
 
@@ -173,16 +203,8 @@ def test_get_loss_mixed_ratio_batches():
                                         mask.double(), gam, [4, 1], dref.V_PREDICTION, dref.DDPM, shifted=True, power=1,
                                         mixed_ratio=mr)
     oloss.mean().backward()
-    assert nc.rel(loss.detach().cpu().double(), oloss.detach()) <= 5e-3
-    mags = sorted(float(P[k].grad.abs().max()) for k in P)
-    floor = 1e-2 * mags[len(mags) // 2]
-    bad = {}
-    for k, p in pipe.get_model().vision_model.named_parameters():
-        ref = P[k].grad
-        e = float((p.grad.cpu().double() - ref).abs().max() / max(float(ref.abs().max()), floor))
-        if not e <= 3e-2:
-            bad[k] = e
-    assert not bad, bad
+    _calibrated_loss_check(pipe, oracle, sd, loss, P, oloss, images, [e.cpu() for e in eps], time.cpu(), lm, mask, [4, 1],
+                           shifted=True, mixed_ratio=mr)
 
 
 @pytest.mark.parametrize("mode,ratio,vmax", [("DYNAMIC", 0.995, 100.0), ("DYNAMIC_IF", 0.95, 1.5)])

@@ -1,10 +1,12 @@
 """Native denoiser parity on B200 against the fp64 oracle (tiny UNet and 2-level NestedUNet):
 outputs, every intermediate residual-stream activation, and every parameter gradient.
 
-Tolerances (max|delta| / max|ref|): the engine multiplies fp16-rounded operands (11-bit significand,
-the same as the TF32 path the reference itself runs on GPUs, train_parallel.py:18-19) with fp32
-accumulation, so 3e-3 on outputs/activations and 2e-2 on gradients are the asserted bounds; measured
-values are ~1e-3 and <=1.5e-2 (profiles/r01_net_parity_tiny.log)."""
+Bounds are stated against the reference's own GPU arithmetic, measured in the same run with the same metric
+(max|delta| / max|ref| against the fp64 oracle): the oracle in fp32 on the B200 with TF32 enabled, which is what the
+reference trains with (clis/train_parallel.py:18-19). Measured (profiles/r02_net_parity_tiny.log): outputs 1.1-1.5e-3
+vs 1.0-1.3e-3 for reference-TF32, gradient median 2.5-2.7e-3 vs 1.9-2.0e-3, worst single gradient 2.3x its
+reference-TF32 error. Asserted: outputs and activations <= max(1e-3, 1.75 x reference-TF32), gradient median <= 1.5 x,
+every gradient <= 3.5 x max(its reference-TF32 error, the reference-TF32 median)."""
 import os
 
 import numpy as np
@@ -20,11 +22,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 @pytest.mark.parametrize("kind", ["unet", "nested"])
 def test_forward_backward_vs_oracle(kind):
     r = nc.run_case(kind, verbose=False)
-    assert all(v <= 3e-3 for v in r["out"]), r["out"]
-    bad = {k: v for k, v in r["acts"].items() if isinstance(v, str) or v > 3e-3}
-    assert not bad, bad
-    badg = {k: v for k, v in r["grads"].items() if not (v <= 2e-2)}
-    assert not badg, badg
+    nc.assert_calibrated(r)
 
 
 @pytest.mark.parametrize("kind", ["unet", "nested"])
@@ -41,7 +39,7 @@ def test_forward_vs_reference_golden(kind):
         out = model([xi.cuda() for xi in x] if nested else x.cuda(), t.cuda(), lm.cuda(), mask.cuda(), {})
     for i, o in enumerate(out if nested else [out]):
         ref = torch.from_numpy(gold[f"fwd_out{i}"])
-        assert nc.rel(o.cpu(), ref) <= 3e-3
+        assert nc.rel(o.cpu(), ref) <= 2.5e-3  # ~1.75 x the reference-TF32 error of these outputs (1.0-1.3e-3)
 
 
 def test_fresh_model_outputs_exact_zero():
