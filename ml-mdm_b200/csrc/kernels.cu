@@ -118,7 +118,9 @@ __device__ __forceinline__ void reduce_over_subs(float4 (&v)[K], const LaneMap& 
 
 inline int pixel_chunks(int N, int HW, int ppi_hint, int per_sm = 8) {
   long long want = cdiv(per_sm * 148, N);
-  long long maxc = cdiv(HW, ppi_hint > 0 ? ppi_hint : 1);
+  // at least ~32 pixel passes per CTA: every CTA pays a prologue (per-channel coefficients) and ends with atomics onto
+  // the same few addresses -- at 16x16 pixels and batch 16, 74 CTAs per sample made gn_stats a 21 us kernel for 2 us of data
+  long long maxc = std::max<long long>(1, HW / (32ll * (ppi_hint > 0 ? ppi_hint : 1)));
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   if (want > 65535) want = 65535;
@@ -1738,7 +1740,7 @@ static void rs_set_smem(K kernel, int bytes) {
 static int staged_chunks(int N, int HW, int pix, int smem_bytes) {
   int resident = std::min(4, std::max(1, (220 * 1024) / (smem_bytes + 6 * 1024)));
   long long want = (static_cast<long long>(resident) * 148) / N;
-  const long long maxc = cdiv(HW, pix);
+  const long long maxc = std::max<long long>(1, HW / (3ll * pix));  // >= 3 chunks per CTA (ring depth; prologue amortised)
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   return static_cast<int>(want);
