@@ -775,7 +775,7 @@ struct Net {
       Param &fw1 = P(a.pre + ".ffn.1.weight"), &fb1 = P(a.pre + ".ffn.1.bias");
       Param &fw3 = P(a.pre + ".ffn.3.weight"), &fb3 = P(a.pre + ".ffn.3.bias");
       g2 = gn_fwd(Src2{x1->p, nullptr, C, 0}, B, T, 32, fw0, fb0, nullptr, 0, 0, 0, false);
-      u16 = E.alloc<__half>(rows * 4 * C);
+      u16 = E.training ? E.alloc<__half>(rows * 4 * C) : nullptr;  // pre-activation: only the backward needs it
       gl16 = E.alloc<__half>(rows * 4 * C);
       {
         Epi e;
