@@ -17,5 +17,7 @@ done
 for p in "${pids[@]}"; do wait $p; done
 OBJS=""
 for f in gemm_tc gemm_persistent kernels engine net capi diffusion attention optim; do [ -f build/$f.o ] && OBJS="$OBJS build/$f.o"; done
-nvcc -arch=sm_100a -shared -o $OUT $OBJS -lcudart
+# link to a temporary name and rename: a concurrent snapshot (gpurun) or loader never sees a half-written library
+nvcc -arch=sm_100a -shared -o $OUT.tmp $OBJS -lcudart
+mv -f $OUT.tmp $OUT
 echo "built $OUT"

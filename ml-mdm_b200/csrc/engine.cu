@@ -97,6 +97,40 @@ float* Engine::grad_buf(Act* a, int* acc) {
   return a->g;
 }
 
+cudaEvent_t Engine::next_event() {
+  if (ev_next == events.size()) {
+    cudaEvent_t e = nullptr;
+    MDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    events.push_back(e);
+  }
+  return events[ev_next++];
+}
+void Engine::side_begin() {
+  if (!side_enabled) return;
+  if (side == nullptr) MDM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  cudaEvent_t e = next_event();
+  MDM_CUDA(cudaEventRecord(e, st));
+  MDM_CUDA(cudaStreamWaitEvent(side, e, 0));
+  main_saved = st;
+  st = side;
+  side_active = true;
+}
+void Engine::side_end() {
+  if (!side_enabled || main_saved == nullptr) return;
+  st = main_saved;
+  main_saved = nullptr;
+}
+void Engine::side_join() {
+  if (main_saved != nullptr) side_end();
+  if (!side_active) return;
+  cudaEvent_t e = next_event();
+  MDM_CUDA(cudaEventRecord(e, side));
+  MDM_CUDA(cudaStreamWaitEvent(st, e, 0));
+  side_active = false;
+  for (void* p : deferred) pool.release(p);
+  deferred.clear();
+}
+
 namespace {
 
 int round16(int n) { return (n + 15) / 16 * 16; }

@@ -105,6 +105,33 @@ struct Engine {
   float* d_inv_scale = nullptr;
   float* d_amax = nullptr;
 
+  // ---- side stream for weight gradients. A weight gradient feeds nothing else in the step, so its kernels (the
+  // wgrad GEMM, its memset and un-pack) can run beside the data-gradient / GroupNorm-backward chain of the same layer
+  // instead of in front of it. In a captured backward this turns the linear chain of ~1.5 k nodes into a graph with
+  // parallel branches. It pays when the step is bound by per-kernel latency (1 sample per GPU: ~2.5 k launches of
+  // ~20 us); with a full GPU the co-running kernels just take SMs from the persistent GEMM, so it is switched on per
+  // step by the batch size (Net::forward, MDM_SIDE_WGRAD=0|1 overrides).
+  bool side_enabled = false;
+  bool side_active = false;  // side work was forked since the last join
+  cudaStream_t side = nullptr;
+  cudaStream_t main_saved = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t ev_next = 0;
+  std::vector<void*> deferred;  // buffers released while side work may still read them
+  cudaEvent_t next_event();
+  // from here on `st` is the side stream, ordered after everything enqueued on the main stream so far
+  void side_begin();
+  // back to the main stream (the side work keeps running)
+  void side_end();
+  // main stream waits for the side work; buffers released meanwhile go back to the pool
+  void side_join();
+  // release that is safe while side work is in flight
+  void rel(void* p) {
+    if (p == nullptr) return;
+    if (side_active) deferred.push_back(p);
+    else pool.release(p);
+  }
+
   template <typename T>
   T* alloc(long long n) {
     return static_cast<T*>(pool.alloc(static_cast<size_t>(n) * sizeof(T)));

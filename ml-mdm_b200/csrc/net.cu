@@ -116,6 +116,8 @@ struct Net {
   }
 
   ~Net() {
+    for (cudaEvent_t e : eng.events) cudaEventDestroy(e);
+    if (eng.side != nullptr) cudaStreamDestroy(eng.side);
     for (auto& r : graphs) free_rec(r);
     if (cap_st != nullptr) cudaStreamDestroy(cap_st);
     for (void* p : persistent) cudaFree(p);
@@ -413,11 +415,13 @@ struct Net {
       colsum_f16(dy16, M, N, b->g, inv_scale(), eng.st);
     }
     if (W.g != nullptr) {
+      eng.side_begin();
       Epi e;
       e.out_f32 = W.g;
       e.alpha_dev = inv_scale();
       e.atomic_ok = true;
       eng.gemm_tn(dy16, ldy, x16, ldx, N, K, M, e);
+      eng.side_end();
     }
     if (dx32 != nullptr) {
       Epi e;
@@ -431,9 +435,11 @@ struct Net {
   // wtmp must hold 36 * cin * cout floats.
   void conv_wgrad_into(const __half* dy16, int ldy, const __half* x16, int ldx, int N, int H, int W, int cin, int cout,
                        float* wtmp, Param& w) {
+    eng.side_begin();  // beside the data-gradient chain of the same layer (engine.cuh); joined at the end of the closure
     const bool folded = eng.conv3x3_wgrad(dy16, ldy, x16, ldx, N, H, W, cin, cout, wtmp, w.w16f != nullptr);
     if (folded) unpack_conv_wgrad_fold(wtmp, w.g, cout, cin, inv_scale(), eng.st);
     else unpack_conv_wgrad(wtmp, w.g, cout, cin, 9, cin, inv_scale(), eng.st);
+    eng.side_end();
   }
 
   struct GnOut {
@@ -485,8 +491,8 @@ struct Net {
       }
     }
     gn_bwd_apply(x, dy, dy_f16 ? 1 : 0, N, HW, G, sums, gw.w, gb.w, film, film_ld, film_off, silu, pg, extra, d, eng.st);
-    eng.pool.release(ab);
-    eng.pool.release(pg);
+    eng.rel(ab);
+    eng.rel(pg);
   }
 
   // ---------------------------------------------------------------- ResNet (unet.py:223-238)
@@ -530,13 +536,13 @@ struct Net {
       eng.conv3x3_fwd(g2.y16, cout, N, H, W, cout, c2w.w16, cout, e, c2w.w16f, c2w.bias_f);
     }
     if (!eng.training) {
-      eng.pool.release(g1.y16);
-      eng.pool.release(g1.raw16);
-      eng.pool.release(g1.sums);
-      eng.pool.release(g2.y16);
-      eng.pool.release(g2.sums);
-      eng.pool.release(h);
-      eng.pool.release(sproj);
+      eng.rel(g1.y16);
+      eng.rel(g1.raw16);
+      eng.rel(g1.sums);
+      eng.rel(g2.y16);
+      eng.rel(g2.sums);
+      eng.rel(h);
+      eng.rel(sproj);
       return out;
     }
     const LevelSpec* Lp = &L;
@@ -569,7 +575,7 @@ struct Net {
       float* dfilm = E.alloc<float>(2ll * N * cout);
       gn_bwd(Src2{h, nullptr, cout, 0}, da2, true, N, HW, G, g2.sums, n2w, n2b, ls->film, Lp->film_total, r.film_off, 1,
              dfilm, nullptr, nullptr, nullptr, dh16, c1b.g);
-      E.pool.release(da2);
+      E.rel(da2);
       // time layer: film = silu(temb) Wt^T + bt  (batch rows)
       {
         __half* df16 = E.alloc<__half>(2ll * N * cout);
@@ -578,8 +584,8 @@ struct Net {
         ls->dstemb_init = true;
         linear_bwd(df16, 2 * cout, N, 2 * cout, Lp->c.temporal_dim, ls->stemb16, Lp->c.temporal_dim, tlw, nullptr,
                    false, ls->dstemb, acc);
-        E.pool.release(df16);
-        E.pool.release(dfilm);
+        E.rel(df16);
+        E.rel(dfilm);
       }
       // conv1
       if (c1w.g != nullptr) conv_wgrad_into(dh16, cout, g1.y16, cin, N, H, W, cin, cout, wtmp, c1w);
@@ -589,19 +595,21 @@ struct Net {
         e.out_f16 = da1;
         E.conv3x3_dgrad(dh16, cout, N, H, W, cout, c1w.w16, cin, e, c1w.w16f);
       }
-      E.pool.release(dh16);
+      E.rel(dh16);
       // norm1 + SiLU -> x (and skip). Identity residual folds in as `extra`.
       gn_bwd(src, da1, true, N, HW, G, g1.sums, n1w, n1b, nullptr, 0, 0, 1, nullptr, proj ? nullptr : out->g, x, skip);
-      E.pool.release(da1);
+      E.rel(da1);
       if (proj) {
         Param &c3w = P(r.pre + ".conv3.weight"), &c3b = P(r.pre + ".conv3.bias");
         if (c3b.g != nullptr) axpy_f32(c3b.g, bias_scratch, 1.f, cout, 1, E.st);
         if (c3w.g != nullptr) {
+          E.side_begin();
           Epi e;
           e.out_f32 = c3w.g;
           e.alpha_dev = inv_scale();
           e.atomic_ok = true;
           E.gemm_tn(d16, cout, g1.raw16, cin, cout, cin, static_cast<int>(rows), e);
+          E.side_end();
         }
         // dX (+)= d16 * W3, split over the two concat sources
         {
@@ -619,10 +627,10 @@ struct Net {
           E.gemm_nn(d16, cout, c3w.w16 + x->c, cin, static_cast<int>(rows), skip->c, cout, e);
         }
       }
-      E.pool.release(wtmp);
-      E.pool.release(d16);
-      E.pool.release(bias_scratch);
-      E.pool.release(out->g);
+      E.rel(wtmp);
+      E.rel(d16);
+      E.rel(bias_scratch);
+      E.rel(out->g);
     });
     return out;
   }
@@ -726,7 +734,7 @@ struct Net {
         gemm_batched(Q, Kk, T, T, d, nh, B, e, Tp, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp);
       }
       softmax_rows(sc, Pm, nrow, T, Tp, nullptr, 1, E.st);
-      E.pool.release(sc);
+      E.rel(sc);
       BOp Pk{Pm, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, false};
       if (!cross) {
         Epi e;
@@ -748,7 +756,7 @@ struct Net {
           gemm_batched(Q, Kc, T, S, d, nh, B, e3, Sp, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp);
         }
         softmax_rows(scc, Pc, nrow, S, Sp, cs.cross_mask, static_cast<long long>(nh) * T, E.st);
-        E.pool.release(scc);
+        E.rel(scc);
         BOp Pck{Pc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, false};
         {
           Epi e4;
@@ -756,7 +764,7 @@ struct Net {
           e4.out_f16 = h16;
           gemm_batched(Pck, Vc, T, d, S, nh, B, e4, C, d, static_cast<long long>(T) * C);
         }
-        E.pool.release(hs32);
+        E.rel(hs32);
       }
     }
     Act* x1 = E.new_act(B, H, W, C);
@@ -795,12 +803,12 @@ struct Net {
       }
     }
     if (!E.training) {
-      E.pool.release(g1.y16); E.pool.release(g1.sums); E.pool.release(qkv); E.pool.release(Pm);
-      E.pool.release(h16); E.pool.release(cn16); E.pool.release(lnstats); E.pool.release(kv); E.pool.release(Pc);
-      E.pool.release(oself); E.pool.release(astats);
+      E.rel(g1.y16); E.rel(g1.sums); E.rel(qkv); E.rel(Pm);
+      E.rel(h16); E.rel(cn16); E.rel(lnstats); E.rel(kv); E.rel(Pc);
+      E.rel(oself); E.rel(astats);
       if (a.ffn) {
-        E.pool.release(g2.y16); E.pool.release(g2.sums); E.pool.release(u16); E.pool.release(gl16);
-        E.pool.release(x1->p);
+        E.rel(g2.y16); E.rel(g2.sums); E.rel(u16); E.rel(gl16);
+        E.rel(x1->p);
       }
       return out;
     }
@@ -826,25 +834,27 @@ struct Net {
           e.gelu_grad_src = u16;
           E.gemm_nn(d16, C, fw3.w16, 4 * C, irows, 4 * C, C, e);
         }
-        E.pool.release(d16);
+        E.rel(d16);
         float* dm32 = E.alloc<float>(rows * C);
         linear_bwd(du16, 4 * C, irows, 4 * C, C, g2.y16, C, fw1, &fb1, true, dm32, 0);
-        E.pool.release(du16);
+        E.rel(du16);
         gn_bwd(Src2{x1->p, nullptr, C, 0}, dm32, false, B, T, 32, g2.sums, fw0, fb0, nullptr, 0, 0, 0, nullptr, out->g, x1,
                nullptr);
-        E.pool.release(dm32);
-        E.pool.release(out->g);
+        E.rel(dm32);
+        E.rel(out->g);
       }
       if (x1->g == nullptr) return;
       // proj_out
       __half* d16 = E.alloc<__half>(rows * C);
       cast_colsum(x1->g, d16, rows, C, pb.g, inv_scale(), E.st);
       if (pw.g != nullptr) {
+        E.side_begin();
         Epi e;
         e.out_f32 = pw.g;
         e.alpha_dev = inv_scale();
         e.atomic_ok = true;
         E.gemm_tn(d16, C, h16, C, C, C, irows, e);
+        E.side_end();
       }
       __half* dh16 = E.alloc<__half>(rows * C);
       {
@@ -852,7 +862,7 @@ struct Net {
         e.out_f16 = dh16;
         E.gemm_nn(d16, C, pw.w16, C, irows, C, C, e);
       }
-      E.pool.release(d16);
+      E.rel(d16);
       __half* dqkv = E.alloc<__half>(rows * 3 * C);
       __half* dkv = nullptr;
       float* dq32 = nullptr;
@@ -863,7 +873,7 @@ struct Net {
         dq32 = E.alloc<float>(rows * C);
         attention_backward(qkv, kv, cross ? cs.cross_mask : nullptr, dh16, h16, oself, astats, B, T, S, C, nh, Dterm, dq32,
                            dqkv, dkv, E.st);
-        E.pool.release(Dterm);
+        E.rel(Dterm);
       } else {
         BOp Q{qkv, d, T, 3ll * C, 3 * nh, d, static_cast<long long>(T) * 3 * C, 0, false};
         BOp Qm = Q; Qm.mn = true;
@@ -889,7 +899,7 @@ struct Net {
         }
         __half* dS = E.alloc<__half>(nrow * Tp);
         softmax_bwd_rows(Pm, dP, dS, nrow, T, Tp, alpha, E.st);
-        E.pool.release(dP);
+        E.rel(dP);
         BOp dSk{dS, T, T, Tp, nh, static_cast<long long>(T) * Tp, static_cast<long long>(nh) * T * Tp, 0, false};
         BOp dSm = dSk; dSm.mn = true;
         // dQ = dS K (+ cross term below)
@@ -910,7 +920,7 @@ struct Net {
           e.out_f16 = dqkv + C;
           gemm_batched(dSm, Qm, T, d, T, nh, B, e, 3 * C, d, qkv_b);
         }
-        E.pool.release(dS);
+        E.rel(dS);
         if (cross) {
           Param &lw = P(a.pre + ".norm_cond.weight"), &lb = P(a.pre + ".norm_cond.bias");
           Param &kw = P(a.pre + ".kv_cond.weight"), &kb = P(a.pre + ".kv_cond.bias");
@@ -934,7 +944,7 @@ struct Net {
           }
           __half* dSc = E.alloc<__half>(nrow * Sp);
           softmax_bwd_rows(Pc, dPc, dSc, nrow, S, Sp, alpha, E.st);
-          E.pool.release(dPc);
+          E.rel(dPc);
           BOp dSck{dSc, S, T, Sp, nh, static_cast<long long>(T) * Sp, static_cast<long long>(nh) * T * Sp, 0, false};
           BOp dScm = dSck; dScm.mn = true;
           {  // dQ = dq32 + dSc Kc -> fp16
@@ -948,7 +958,7 @@ struct Net {
             e.out_f16 = dkv;
             gemm_batched(dScm, Qm, S, d, T, nh, B, e, 2 * C, d, kv_b);
           }
-          E.pool.release(dSc);
+          E.rel(dSc);
         }
 
       }
@@ -969,8 +979,8 @@ struct Net {
           E.gemm_tn(dkv, 2 * C, cs.xhat16, cd, 2 * C, cd, static_cast<int>(crow), e);
         }
         unfold_ln_grads(dWf, dbf, kw.w, lw.w, lb.w, kw.g, lw.g, lb.g, 2 * C, cd, E.st);
-        E.pool.release(dWf);
-        E.pool.release(dbf);
+        E.rel(dWf);
+        E.rel(dbf);
         const bool whole = B == cs.B;  // a level that ran only part of the batch touches the leading rows only
         if (cs.dxhat == nullptr) {
           cs.dxhat = whole ? E.alloc<float>(crow * cd) : E.zeros_f32(static_cast<long long>(cs.B) * S * cd);
@@ -983,17 +993,17 @@ struct Net {
           E.gemm_nn(dkv, 2 * C, kw.w16, cd, static_cast<int>(crow), cd, 2 * C, e);
         }
         cs.dxhat_init = true;
-        E.pool.release(dkv);
+        E.rel(dkv);
       }
       // qkv conv + norm
       float* dn32 = E.alloc<float>(rows * C);
       linear_bwd(dqkv, 3 * C, irows, 3 * C, C, g1.y16, C, qw, &qb, true, dn32, 0);
-      E.pool.release(dqkv);
-      E.pool.release(dh16);
-      E.pool.release(dq32);
+      E.rel(dqkv);
+      E.rel(dh16);
+      E.rel(dq32);
       gn_bwd(Src2{x->p, nullptr, C, 0}, dn32, false, B, T, 32, g1.sums, nw, nb, nullptr, 0, 0, 0, nullptr, x1->g, x, nullptr);
-      E.pool.release(dn32);
-      E.pool.release(x1->g);
+      E.rel(dn32);
+      E.rel(x1->g);
     });
     return out;
   }
@@ -1013,7 +1023,7 @@ struct Net {
     e.out_f32 = y->p;
     E.gemm_nt(col, 9ll * C, w.w16, 9ll * C, static_cast<int>(orow), C, 9 * C, e);
     if (!E.training) {
-      E.pool.release(col);
+      E.rel(col);
       return y;
     }
     E.tape.push_back([=]() {
@@ -1029,7 +1039,7 @@ struct Net {
         e.atomic_ok = true;
         E.gemm_tn(d16, C, col, 9ll * C, C, 9 * C, static_cast<int>(orow), e);
         unpack_conv_wgrad(wtmp, w.g, C, C, 9, C, inv_scale(), E.st);
-        E.pool.release(wtmp);
+        E.rel(wtmp);
       }
       float* dcol = E.alloc<float>(orow * 9 * C);
       {
@@ -1040,9 +1050,9 @@ struct Net {
       int acc = 0;
       float* dx = E.grad_buf(x, &acc);
       col2im3x3(dcol, dx, acc, N, H, W, C, 2, E.st);
-      E.pool.release(dcol);
-      E.pool.release(d16);
-      E.pool.release(y->g);
+      E.rel(dcol);
+      E.rel(d16);
+      E.rel(y->g);
     });
     return y;
   }
@@ -1077,13 +1087,13 @@ struct Net {
     if (w.g != nullptr) {
       float* wtmp = E.alloc<float>((Engine::fold_ok(Cin, Cout) ? 36ll : 9ll) * Cin * Cout);
       conv_wgrad_into(d16, Cout, x16, Cin, N, H, W, Cin, Cout, wtmp, w);
-      E.pool.release(wtmp);
+      E.rel(wtmp);
     }
     float* dx = E.alloc<float>(rows * Cin);
     Epi e;
     e.out_f32 = dx;
     E.conv3x3_dgrad(d16, Cout, N, H, W, Cout, w.w16, Cin, e, w.w16f);
-    E.pool.release(d16);
+    E.rel(d16);
     return dx;
   }
 
@@ -1094,7 +1104,7 @@ struct Net {
     upsample2x_f16(x->p, u16, N, H, W, C, E.st);
     Act* y = conv_act(b.pre + ".resample.weight", b.pre + ".resample.bias", u16, N, 2 * H, 2 * W, C, C, nullptr);
     if (!E.training) {
-      E.pool.release(u16);
+      E.rel(u16);
       return y;
     }
     E.tape.push_back([=]() {
@@ -1104,8 +1114,8 @@ struct Net {
       int acc = 0;
       float* dx = E.grad_buf(x, &acc);
       upsample2x_bwd(du, dx, acc, N, H, W, C, E.st);
-      E.pool.release(du);
-      E.pool.release(y->g);
+      E.rel(du);
+      E.rel(y->g);
     });
     return y;
   }
@@ -1176,9 +1186,9 @@ struct Net {
     silu_bwd(rec.h1, dsh, dh1, n, 0, E.st);
     cast_colsum(dh1, d16, B, td, b1.g, inv_scale(), E.st);
     linear_bwd(d16, td, B, td, td / 4, rec.e16, td / 4, w1, nullptr, false, nullptr, 0);
-    E.pool.release(d16);
-    E.pool.release(dsh);
-    E.pool.release(dh1);
+    E.rel(d16);
+    E.rel(dsh);
+    E.rel(dh1);
   }
 
   // forward_conditioning (unet.py:847-865) on the innermost level
@@ -1244,8 +1254,8 @@ struct Net {
           masked_mean_bwd(dy, cs.mask, cs.dcond, cs.dcond_init ? 1 : 0, B, S, cfg.cond_dim, E.st);
           cs.dcond_init = true;
         }
-        E.pool.release(d16);
-        E.pool.release(dy);
+        E.rel(d16);
+        E.rel(dy);
       }
       if (cs.dxhat_init) {
         if (cs.dcond == nullptr) cs.dcond = E.alloc<float>(crow * cfg.cond_dim);
@@ -1259,7 +1269,7 @@ struct Net {
         cast_colsum(cs.dcond, d16, crow, cfg.cond_dim, b.g, inv_scale(), E.st);
         linear_bwd(d16, cfg.cond_dim, static_cast<int>(crow), cfg.cond_dim, cfg.lm_dim, cs.lm16, cfg.lm_dim, w, nullptr,
                    false, nullptr, 0);
-        E.pool.release(d16);
+        E.rel(d16);
       }
     });
   }
@@ -1285,7 +1295,7 @@ struct Net {
                      E.st);
       float* m = embed_mlp_fwd(L.pre + "cond_layers.scale.0", L.pre + "cond_layers.scale.1", m16, B, td, &mrec);
       add_f32(t, t, m, n, E.st);
-      E.pool.release(m);
+      E.rel(m);
     }
     ls->stemb16 = E.alloc<__half>(n);
     silu_f16(t, ls->stemb16, n, E.st);
@@ -1311,7 +1321,7 @@ struct Net {
         axpy_f32(cs.dcemb, dt, 1.f, n, 1, E.st);  // this level's leading rows
         cs.dcemb_init = true;
       }
-      E.pool.release(dt);
+      E.rel(dt);
     });
     return ls;
   }
@@ -1358,18 +1368,18 @@ struct Net {
           e.atomic_ok = true;
           E.gemm_tn(d16, C0, col, 32, C0, 32, static_cast<int>(rows), e);
           unpack_conv_in_wgrad(wtmp, ciw.g, C0, cfg.in_channels, inv_scale(), E.st);
-          E.pool.release(wtmp);
+          E.rel(wtmp);
         }
         if (x_feat != nullptr) {
           int acc = 0;
           float* g = E.grad_buf(x_feat, &acc);
           axpy_f32(g, x->g, 1.f, x->numel(), acc, E.st);
         }
-        E.pool.release(d16);
-        E.pool.release(x->g);
+        E.rel(d16);
+        E.rel(x->g);
       });
     } else {
-      E.pool.release(col);
+      E.rel(col);
     }
 
     // down path
@@ -1402,11 +1412,11 @@ struct Net {
           int acc = 0;
           float* g = E.grad_buf(xo_in, &acc);
           axpy_f32(g, dx16, 1.f, xo_in->numel(), acc, E.st);
-          E.pool.release(dx16);
-          E.pool.release(xin->g);
+          E.rel(dx16);
+          E.rel(xin->g);
         });
       } else {
-        E.pool.release(x16);
+        E.rel(x16);
       }
       Act* feat = level_fwd(li + 1, xin);
       // out_adapter on the leading N samples only: the reference convolves all Bin and slices [:N] (nested_unet.py:208-209),
@@ -1426,13 +1436,13 @@ struct Net {
           axpy_f32(g, df, 1.f, lead, acc, E.st);
           if (!acc && feat->numel() > lead)
             MDM_CUDA(cudaMemsetAsync(g + lead, 0, sizeof(float) * (feat->numel() - lead), E.st));
-          E.pool.release(df);
+          E.rel(df);
           g = E.grad_buf(xo_in, &acc);
           axpy_f32(g, xn->g, 1.f, xo_in->numel(), acc, E.st);
-          E.pool.release(xn->g);
+          E.rel(xn->g);
         });
       } else {
-        E.pool.release(f16);
+        E.rel(f16);
       }
       x = xn;
     }
@@ -1458,7 +1468,7 @@ struct Net {
       e.out_f32 = o;
       E.conv3x3_fwd(g.y16, Cf, B, R, R, Cf, ow.w16, oc, e, ow.w16f, ow.bias_f);
       nhwc_to_nchw(o, oc, io->out[li], B, oc, HW, E.st);
-      E.pool.release(o);
+      E.rel(o);
       outs[li].res = R;
       outs[li].batch = B;
       if (E.training) {
@@ -1476,7 +1486,7 @@ struct Net {
             float* wtmp = E.alloc<float>(9ll * Cf * oc);
             E.conv3x3_wgrad(orec->d16, 8, g.y16, Cf, B, R, R, Cf, oc, wtmp);
             unpack_conv_wgrad(wtmp, ow.g, oc, Cf, 9, Cf, inv_scale(), E.st);
-            E.pool.release(wtmp);
+            E.rel(wtmp);
           }
           __half* da = E.alloc<__half>(rows * Cf);
           Epi e;
@@ -1484,12 +1494,12 @@ struct Net {
           E.conv3x3_dgrad(orec->d16, 8, B, R, R, oc, ow.w16, Cf, e);
           gn_bwd(Src2{feat->p, nullptr, Cf, 0}, da, true, B, HW, Lp->c.groups, g.sums, nw, nb, nullptr, 0, 0, 1, nullptr,
                  nullptr, feat, nullptr);
-          E.pool.release(da);
-          E.pool.release(bs);
+          E.rel(da);
+          E.rel(bs);
         });
       } else {
-        E.pool.release(g.y16);
-        E.pool.release(g.sums);
+        E.rel(g.y16);
+        E.rel(g.sums);
       }
     }
     return feat;
@@ -1515,6 +1525,12 @@ struct Net {
       MDM_CHECK(io->res[l] % (1 << (cfg.levels[l].num_res - 1)) == 0, "resolution not divisible by the level's downsampling");
     }
     if (cfg.cond_dim > 0) MDM_CHECK(io->lm != nullptr && io->tokens > 0, "conditioning required");
+    {  // side-stream weight gradients only where the step is latency-bound (engine.cuh)
+      static const char* sw = getenv("MDM_SIDE_WGRAD");
+      const long long core_pixels = static_cast<long long>(io->batch) * io->res[cfg.num_levels - 1] * io->res[cfg.num_levels - 1];
+      eng.side_enabled = sw != nullptr ? atoi(sw) != 0 : core_pixels <= 4ll * 64 * 64;
+      eng.ev_next = 0;
+    }
     prepare_weights();
     conditioning_fwd();
     level_fwd(0, nullptr);
@@ -1836,12 +1852,14 @@ struct Net {
       ~Guard() {
         n->replay_idx = -1;
         n->final_lo = UINTPTR_MAX;
+        n->eng.side_end();  // (an exception inside a side scope must not leave the engine on the side stream)
       }
     } guard{this};
     for (int i = n - 1; i >= 0; --i) {
       replay_idx = i;
       cur_lookup.clear();
       eng.tape[i]();
+      eng.side_join();  // weight-gradient work of this closure is ordered before anything later (and before a report)
       std::vector<int>& seen = learned[i];
       for (int idx : cur_lookup)
         if (std::find(seen.begin(), seen.end(), idx) == seen.end()) seen.push_back(idx);
