@@ -108,9 +108,10 @@ struct Engine {
   // ---- side stream for weight gradients. A weight gradient feeds nothing else in the step, so its kernels (the
   // wgrad GEMM, its memset and un-pack) can run beside the data-gradient / GroupNorm-backward chain of the same layer
   // instead of in front of it. In a captured backward this turns the linear chain of ~1.5 k nodes into a graph with
-  // parallel branches. It pays when the step is bound by per-kernel latency (1 sample per GPU: ~2.5 k launches of
-  // ~20 us); with a full GPU the co-running kernels just take SMs from the persistent GEMM, so it is switched on per
-  // step by the batch size (Net::forward, MDM_SIDE_WGRAD=0|1 overrides).
+  // parallel branches. Measured (profiles/r02_side_wgrad.txt): cc12m_1024x1024 at 1 / 2 / 4 samples per GPU 43.0 ->
+  // 41.0, 57.4 -> 55.6, 86.2 -> 84.1 ms (the step is bound by per-kernel latency there), cc12m_64x64 b64 139.0 -> 137.6,
+  // cc12m_256x256 b32 140.8 -> 139.4 ms. MDM_SIDE_WGRAD=0 turns it off. Buffers the side work reads are released
+  // through rel() (deferred to the join) and must not be overwritten by the main stream before it.
   bool side_enabled = false;
   bool side_active = false;  // side work was forked since the last join
   cudaStream_t side = nullptr;

@@ -1184,8 +1184,11 @@ struct Net {
     linear_bwd(d16, td, B, td, td, rec.sh16, td, w2, nullptr, false, dsh, 0);
     float* dh1 = E.alloc<float>(n);
     silu_bwd(rec.h1, dsh, dh1, n, 0, E.st);
-    cast_colsum(dh1, d16, B, td, b1.g, inv_scale(), E.st);
-    linear_bwd(d16, td, B, td, td / 4, rec.e16, td / 4, w1, nullptr, false, nullptr, 0);
+    // (a second buffer: the weight-gradient GEMM of layer 2 may still be reading d16 on the side stream)
+    __half* d16b = E.alloc<__half>(n);
+    cast_colsum(dh1, d16b, B, td, b1.g, inv_scale(), E.st);
+    linear_bwd(d16b, td, B, td, td / 4, rec.e16, td / 4, w1, nullptr, false, nullptr, 0);
+    E.rel(d16b);
     E.rel(d16);
     E.rel(dsh);
     E.rel(dh1);
@@ -1525,10 +1528,9 @@ struct Net {
       MDM_CHECK(io->res[l] % (1 << (cfg.levels[l].num_res - 1)) == 0, "resolution not divisible by the level's downsampling");
     }
     if (cfg.cond_dim > 0) MDM_CHECK(io->lm != nullptr && io->tokens > 0, "conditioning required");
-    {  // side-stream weight gradients only where the step is latency-bound (engine.cuh)
+    {  // weight gradients on a side stream (engine.cuh); MDM_SIDE_WGRAD=0 keeps everything on one stream
       static const char* sw = getenv("MDM_SIDE_WGRAD");
-      const long long core_pixels = static_cast<long long>(io->batch) * io->res[cfg.num_levels - 1] * io->res[cfg.num_levels - 1];
-      eng.side_enabled = sw != nullptr ? atoi(sw) != 0 : core_pixels <= 4ll * 64 * 64;
+      eng.side_enabled = sw != nullptr ? atoi(sw) != 0 : true;
       eng.ev_next = 0;
     }
     prepare_weights();
