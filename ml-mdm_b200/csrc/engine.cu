@@ -106,7 +106,7 @@ cudaEvent_t Engine::next_event() {
   return events[ev_next++];
 }
 void Engine::side_begin() {
-  if (!side_enabled) return;
+  if (!side_enabled || !capturing) return;
   if (side == nullptr) MDM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
   cudaEvent_t e = next_event();
   MDM_CUDA(cudaEventRecord(e, st));
@@ -116,7 +116,7 @@ void Engine::side_begin() {
   side_active = true;
 }
 void Engine::side_end() {
-  if (!side_enabled || main_saved == nullptr) return;
+  if (main_saved == nullptr) return;
   st = main_saved;
   main_saved = nullptr;
 }

@@ -112,7 +112,12 @@ struct Engine {
   // 41.0, 57.4 -> 55.6, 86.2 -> 84.1 ms (the step is bound by per-kernel latency there), cc12m_64x64 b64 139.0 -> 137.6,
   // cc12m_256x256 b32 140.8 -> 139.4 ms. MDM_SIDE_WGRAD=0 turns it off. Buffers the side work reads are released
   // through rel() (deferred to the join) and must not be overwritten by the main stream before it.
+  // Only while a backward is being CAPTURED: there the fork / join events become explicit graph edges. Run eagerly
+  // (first step of a signature, MDM_NO_GRAPH) everything stays on the caller's stream -- ordering a non-blocking side
+  // stream against torch's legacy default stream by events did not hold up in the tests (later main-stream readers saw
+  // incomplete weight gradients), and the eager path is not where the time goes.
   bool side_enabled = false;
+  bool capturing = false;
   bool side_active = false;  // side work was forked since the last join
   cudaStream_t side = nullptr;
   cudaStream_t main_saved = nullptr;

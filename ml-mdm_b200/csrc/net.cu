@@ -1769,6 +1769,7 @@ struct Net {
       for (int l = 0; l < cfg.num_levels; ++l) sg.dout[l] = (mask >> l) & 1 ? r.dout[l] : nullptr;
       const unsigned long long k0 = g_launch_count;
       MDM_CUDA(cudaStreamBeginCapture(cap_st, cudaStreamCaptureModeRelaxed));
+      eng.capturing = true;  // weight gradients may fork onto the side stream (graph branches)
       try {
         // a reported range closes the current segment: its graph ends here and the next one begins
         seg_cut = [&](uintptr_t lo, uintptr_t hi) {
@@ -1778,10 +1779,12 @@ struct Net {
         };
         backward_body(&sg, cap_st);
         seg_cut = nullptr;
+        eng.capturing = false;
         r.bwd.push_back(end_capture());
         r.bwd_ranges.emplace_back(0, 0);
       } catch (...) {
         seg_cut = nullptr;
+        eng.capturing = false;
         abort_capture();
         drop_graph(r);
         eng.st = st;
