@@ -1868,7 +1868,7 @@ void cast_colsum(const float* in, __half* out16, long long rows, int C, float* c
 }
 void colsum_f16(const __half* in, long long rows, int C, float* colsum, const float* inv_scale, cudaStream_t st) {
   static const bool wide = getenv("MDM_COLSUM_LEGACY") == nullptr;
-  if (wide && C % 8 == 0 && rows >= 1024) {
+  if (wide && C % 8 == 0 && rows >= 64) {
     const int ctiles = static_cast<int>(cdiv(C, 8 * TPB));
     const int Ct = std::min(C, 8 * TPB);
     const int lanes = Ct / 8;
