@@ -77,6 +77,9 @@ typedef struct mdm_gemm_params {
   int32_t kfactor; /* MDM_GEMM_CONV_WGRAD only: pixel rows per pipeline stage = 64 * kfactor (0/1: 64). Narrow layers
                     * (<= 64 channels) move only 4-8 KB per 64-pixel stage, so the stage round trip, not HBM, sets
                     * the pace; 256-pixel stages cut the round trips four-fold. Needs a PW x PH = 64 * kfactor patch. */
+  int32_t pair; /* filled by the launcher: 1 = CTA pairs (tcgen05 cta_group::2). Two adjacent M tiles run as one
+                 * M = 256 instruction: each CTA stages its 128 rows of A and HALF of the B tile, so the shared-memory
+                 * traffic per flop drops by a third -- what bounds the one-CTA form on wide tiles. */
 } mdm_gemm_params;
 
 /* Measurement aid for bench.py's roofline leg: while enabled every launch of the tcgen05 GEMM kernel

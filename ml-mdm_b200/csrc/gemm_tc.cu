@@ -34,7 +34,9 @@ constexpr int SMEM_BUDGET = 99 * 1024;  // two CTAs per SM: one runs its epilogu
 
 constexpr int NUM_THREADS = 256;  // warps 0-3: TMA / MMA / epilogue, warps 4-7: epilogue only
 
-template <bool A_MN, bool B_MN>
+// PAIR is a template parameter because a kernel may not mix cta_group::1 and cta_group::2 tcgen05 instructions (a kernel
+// holding any cta_group::2 instruction only launches with an even cluster size).
+template <bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -52,7 +54,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int nb_alloc = B_MN ? ((p.block_n + 63) / 64) * 64 : p.block_n;
+  // CTA pair (cta_group::2): this CTA stages its own 128 rows of A and its half of the B tile
+  constexpr bool pair = PAIR;
+  const int nb_local = pair ? p.block_n / 2 : p.block_n;
+  const int nb_alloc = B_MN ? ((nb_local + 63) / 64) * 64 : nb_local;
   // weight gradients of narrow layers: kf x 64 pixel rows per stage, and a single A slab when M <= 64
   const int kf = (p.kind == GEMM_CONV_WGRAD && p.kfactor > 1) ? p.kfactor : 1;
   const int slab_bytes = SLAB_BYTES * kf;
@@ -76,8 +81,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Cluster of cs CTAs along the M tiles: same B tile for all of them, each fetches 1/cs of it and multicasts.
   // (TMA moves ~one <= 128-byte row per 3 clocks per SM whatever the row holds; a 128 x 256 tile needs 128 A + 256 B
   // rows per k block against 512 clocks of MMA, so the loads, not the tensor pipe, set the pace without this.)
-  const int cs = p.cluster > 1 ? p.cluster : 1;
-  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const int cs = p.cluster > 1 ? p.cluster : 1;  // (multicast clusters and CTA pairs are mutually exclusive)
+  const uint32_t crank = (cs > 1 || pair) ? cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   const int m_tile = blockIdx.x;
   const int m0 = m_tile * BLOCK_M;
@@ -103,12 +108,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(p.block_n)) tmem_cols <<= 1;
-  if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+  if (warp == 1) {
+    if constexpr (pair) tmem_alloc_2sm(&tmem_base_smem, tmem_cols);
+    else tmem_alloc(&tmem_base_smem, tmem_cols);
+  }
   for (int i = threadIdx.x; i < p.block_n; i += blockDim.x)
     s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();  // peers' barriers exist before anything is multicast to them
+  if (cs > 1 || pair) cluster_sync_all();  // peers' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -127,6 +135,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* sA = smem + stage * stage_bytes;
       uint8_t* sB = sA + a_stage_bytes;
       uint64_t* bar = &full_bar[stage];
+      if constexpr (pair) {
+        // Both CTAs' boxes complete on the LEADER's barrier (armed by the leader alone with both CTAs' bytes): its MMA
+        // reads the two shared memories. This CTA's slot is freed by the leader's multicast commit on empty_bar.
+        const uint32_t lbar = mapa_u32(smem_u32(bar), 0);
+        if (crank == 0) mbar_expect_tx(bar, static_cast<uint32_t>(2 * stage_bytes));
+        const int nh = nb_local;               // B columns of this CTA
+        const int nb0 = n0 + static_cast<int>(crank) * nh;
+        const int nslab = nb_alloc / 64;
+        if (p.kind == GEMM_PLAIN) {
+          if (!A_MN) {
+            tma_load_4d_2sm(sA, &tmA, lbar, kb * BLOCK_K, m0, az1, az2);
+          } else {
+            tma_load_4d_2sm(sA, &tmA, lbar, m0, kb * BLOCK_K, az1, az2);
+            tma_load_4d_2sm(sA + SLAB_BYTES, &tmA, lbar, m0 + 64, kb * BLOCK_K, az1, az2);
+          }
+          if (!B_MN) {
+            tma_load_4d_2sm(sB, &tmBpart, lbar, kb * BLOCK_K, nb0, bz1, bz2);
+          } else {
+            for (int s = 0; s < nslab; ++s)
+              tma_load_4d_2sm(sB + s * SLAB_BYTES, &tmB, lbar, nb0 + 64 * s, kb * BLOCK_K, bz1, bz2);
+          }
+        } else if (p.kind == GEMM_CONV) {
+          const int tap = kb / p.kblocks_c;
+          const int cb = kb - tap * p.kblocks_c;
+          const int kh = (p.taps == 9) ? tap / 3 : 1;
+          const int kw = (p.taps == 9) ? tap % 3 : 1;
+          tma_load_4d_2sm(sA, &tmA, lbar, cb * BLOCK_K, tw * p.PW + kw - 1, th * p.PH + kh - 1, img);
+          const int wt = p.flip ? (p.taps - 1 - tap) : tap;
+          if (!B_MN) {
+            tma_load_4d_2sm(sB, &tmBpart, lbar, cb * BLOCK_K, nb0, tap, 0);
+          } else {
+            for (int s = 0; s < nslab; ++s)
+              tma_load_4d_2sm(sB + s * SLAB_BYTES, &tmB, lbar, nb0 + 64 * s, cb * BLOCK_K, wt, 0);
+          }
+        } else {  // GEMM_CONV_WGRAD
+          const int ptw = kb % p.tiles_w;
+          const int t = kb / p.tiles_w;
+          const int pth = t % p.tiles_h;
+          const int pimg = t / p.tiles_h;
+          const int kh = (p.taps == 9) ? z1 / 3 : 1;
+          const int kw = (p.taps == 9) ? z1 % 3 : 1;
+          tma_load_4d_2sm(sA, &tmA, lbar, m0, ptw * p.PW, pth * p.PH, pimg);
+          if (a_slabs == 2) tma_load_4d_2sm(sA + slab_bytes, &tmA, lbar, m0 + 64, ptw * p.PW, pth * p.PH, pimg);
+          for (int s = 0; s < nslab; ++s)
+            tma_load_4d_2sm(sB + s * slab_bytes, &tmB, lbar, nb0 + 64 * s, ptw * p.PW + kw - 1, pth * p.PH + kh - 1, pimg);
+        }
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        continue;
+      }
       mbar_expect_tx(bar, static_cast<uint32_t>(stage_bytes));
       if (p.kind == GEMM_PLAIN) {
         if (!A_MN) {
@@ -194,9 +254,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0 && nkb > 0) {
-    // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc_f16(BLOCK_M, p.block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  } else if (warp == 1 && lane == 0 && nkb > 0 && !(pair && crank != 0)) {
+    // =========================== MMA issuer (the leader CTA of a pair issues for both) ===========================
+    const uint32_t idesc = make_idesc_f16(pair ? 2 * BLOCK_M : BLOCK_M, p.block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < nkb; ++i) {
@@ -211,7 +271,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                       : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
           const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
                                       : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-          umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if constexpr (pair) umma_f16_2sm(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          else umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
       } else {
         // tall MN-major slabs (kf * 64 pixel rows x 64 columns). With one A slab (M <= 64) the second 64-column
@@ -220,18 +281,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < 4 * kf; ++k) {
           const uint64_t adesc = make_smem_desc_sw128(a_base + k * 2048, a_lbo, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 2048, static_cast<uint32_t>(slab_bytes), 1024);
-          umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if constexpr (pair) umma_f16_2sm(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          else umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
       }
       // frees the smem slot once these MMAs retire -- in every CTA of the cluster, whose producers all write into it
-      if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);
+      if constexpr (pair) umma_commit_2sm(&empty_bar[stage]);
+      else if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);
       else umma_commit(&empty_bar[stage]);
       if (++stage == nstages) {
         stage = 0;
         phase ^= 1;
       }
     }
-    umma_commit(&accum_bar);
+    if constexpr (pair) umma_commit_2sm(&accum_bar);
+    else umma_commit(&accum_bar);
   }
   __syncwarp();
 
@@ -384,7 +448,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) bulk_wait_all();
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (cs > 1 || pair) cluster_sync_all();  // no peer may still arrive on this CTA's barriers after it is gone
+    if (warp == 1) {
+      if constexpr (pair) tmem_dealloc_2sm(tmem_base, tmem_cols);
+      else tmem_dealloc(tmem_base, tmem_cols);
+    }
     return;
   }
 
@@ -474,8 +542,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();  // no peer may still arrive on this CTA's barriers after it is gone
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (cs > 1 || pair) cluster_sync_all();  // no peer may still arrive on this CTA's barriers after it is gone
+  if (warp == 1) {
+    if constexpr (pair) tmem_dealloc_2sm(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -523,12 +594,12 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s, bool f32 = false) {
   return 0;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PAIR>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap& tmBpart,
                 const GemmParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
@@ -539,7 +610,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     cudaEventCreate(&e1);
     cudaEventRecord(e0, stream);
   }
-  if (p.cluster > 1) {
+  if (p.cluster > 1 || p.pair) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(NUM_THREADS);
@@ -547,15 +618,15 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
+    attr[0].val.clusterDim.x = p.pair ? 2u : static_cast<unsigned>(p.cluster);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN>, tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, PAIR>, tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p);
     if (le != cudaSuccess) return static_cast<int>(le);
   } else {
-    gemm_tc_kernel<A_MN, B_MN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p);
+    gemm_tc_kernel<A_MN, B_MN, PAIR><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p);
   }
   if (g_profile) {
     cudaEventRecord(e1, stream);
@@ -587,11 +658,43 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   if (encode_tmap(&tmA, A) != 0) return -20;
   if (encode_tmap(&tmB, B) != 0) return -21;
 
-  const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
   if (p.kind != GEMM_CONV_WGRAD || p.kfactor < 1) p.kfactor = 1;
   const int kf = p.kfactor;
   if (kf > 1 && (!a_mn || !b_mn || p.PW * p.PH != 64 * kf || kf > 4)) return -15;
-  const int stage_bytes = kf > 1 ? ((p.M <= 64 ? 1 : 2) + nb_alloc / 64) * SLAB_BYTES * kf : A_STAGE_BYTES + nb_alloc * 128;
+  int m_tiles;
+  if (p.kind == GEMM_CONV) {
+    m_tiles = p.nimg * p.tiles_h * p.tiles_w;
+  } else {
+    m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  }
+  const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
+
+  // ---- which kernel form. Persistent warp-specialised variant (gemm_persistent.cu) for the non-split, TMA-store
+  // launches. Measured (B200): it wins where the epilogue matters (K <= ~3000: 16384x3072x768 runs at 1048 vs 824
+  // TFLOP/s) and loses on long-K tiles, where two co-resident CTAs hide latency better (8192^3: 1196 vs 1353), and
+  // when the tile count leaves a mostly empty last round.
+  static const bool persistent = getenv("MDM_GEMM_NO_PERSISTENT") == nullptr;
+  static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 96;
+  const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
+  const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
+  const bool persist_shape = persistent && p.block_n >= persist_min_n && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD &&
+                             p.num_kblocks <= 48 && rounds_ok;  // (and a TMA-store epilogue, checked below)
+
+  // ---- CTA pairs (cta_group::2) for the MMA-bound launches of the one-tile form: wide tiles, long contraction.
+  // Each CTA stages 128 rows of A and HALF of the B tile; the leader issues M = 256 instructions for both.
+  // Measured (profiles/r02_pair_sweep.txt, one-tile form, pairs off -> on): 8192^3 1287 -> 1399 TFLOP/s, 8192x768x6912
+  // 1016 -> 1199, 3x3 conv 768->768 @16x16 968 -> 1117, 512->512 @32x32 1135 -> 1265 (cuBLAS bf16 on the same box:
+  // 1340-1556). MDM_GEMM_PAIR=0 turns them off.
+  static const int pair_env = getenv("MDM_GEMM_PAIR") ? atoi(getenv("MDM_GEMM_PAIR")) : 1;
+  p.pair = (pair_env != 0 && m_tiles >= 2 && p.block_n >= 128 && (p.block_n % 32) == 0 && !(kf > 1 && p.M <= 64)) ? 1 : 0;
+
+  auto stage_bytes_of = [&](bool pr) {
+    const int nl = pr ? p.block_n / 2 : p.block_n;
+    const int na = b_mn ? ((nl + 63) / 64) * 64 : nl;
+    return kf > 1 ? ((p.M <= 64 ? 1 : 2) + na / 64) * SLAB_BYTES * kf : A_STAGE_BYTES + na * 128;
+  };
+  const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;  // unpaired
+  int stage_bytes = stage_bytes_of(p.pair != 0);
   static const int budget_kb = getenv("MDM_SMEM_BUDGET_KB") ? atoi(getenv("MDM_SMEM_BUDGET_KB")) : 0;  // dev knob
   // Narrow tiles (N <= 64: the 32/64-channel levels of the 256- and 1024-px nests) do so little work per tile that
   // the fixed per-tile latencies dominate; three co-resident CTAs of the one-tile-per-CTA form hide them better than
@@ -610,13 +713,6 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   p.num_stages = stages;
   size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
 
-  int m_tiles;
-  if (p.kind == GEMM_CONV) {
-    m_tiles = p.nimg * p.tiles_h * p.tiles_w;
-  } else {
-    m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  }
-  const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
   dim3 grid(m_tiles, n_tiles, p.nz1 * p.nz2 * p.nsplit);
   if (grid.y > 65535 || grid.z > 65535) return -14;
 
@@ -691,27 +787,34 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   }
   p.cluster = 1;
 
-  // persistent warp-specialised variant (gemm_persistent.cu) for the non-split, TMA-store launches
-  static const bool persistent = getenv("MDM_GEMM_NO_PERSISTENT") == nullptr;
-  // Measured (B200): the persistent kernel wins where the epilogue matters (K <= ~3000: 16384x3072x768 runs at
-  // 1048 vs 824 TFLOP/s) and loses on long-K tiles, where two co-resident CTAs hide latency better
-  // (8192^3: 1196 vs 1353), and when the tile count leaves a mostly empty last round.
-  {
-    const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
-    const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
-    static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 96;
-    if (persistent && p.block_n >= persist_min_n && p.epi_tma && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD && p.num_kblocks <= 48 && rounds_ok)
-      return launch_gemm_persistent(tmA, tmB, tmO, tmBpart, cs, a_mn, b_mn, p, m_tiles, n_tiles, stream);
+  if (persist_shape && p.epi_tma) {
+    p.pair = 0;
+    return launch_gemm_persistent(tmA, tmB, tmO, tmBpart, cs, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }
 
+  if (p.pair) {
+    cs = 1;
+    if (!b_mn) {  // K-major B: this CTA's box is its half of the tile's rows
+      TmapSpec part = B;
+      part.box[1] = static_cast<uint32_t>(p.block_n / 2);
+      if (encode_tmap(&tmBpart, part) != 0) return -22;
+    }
+    grid.x = static_cast<unsigned>((m_tiles + 1) / 2 * 2);
+  }
   if (cs > 1) {
     p.cluster = cs;
     grid.x = static_cast<unsigned>((m_tiles + cs - 1) / cs * cs);
   }
-  if (!a_mn && !b_mn) return launch_impl<false, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
-  if (!a_mn && b_mn) return launch_impl<false, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
-  if (a_mn && b_mn) return launch_impl<true, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
-  return launch_impl<true, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  if (p.pair) {
+    if (!a_mn && !b_mn) return launch_impl<false, false, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+    if (!a_mn && b_mn) return launch_impl<false, true, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+    if (a_mn && b_mn) return launch_impl<true, true, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+    return launch_impl<true, false, true>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  }
+  if (!a_mn && !b_mn) return launch_impl<false, false, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  if (!a_mn && b_mn) return launch_impl<false, true, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  if (a_mn && b_mn) return launch_impl<true, true, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
+  return launch_impl<true, false, false>(tmA, tmB, tmO, tmBpart, p, grid, smem, stream);
 }
 
 }  // namespace mdm

@@ -65,6 +65,7 @@ class GemmParams(C.Structure):
         ("gelu_grad_src", C.c_void_p),
         ("cluster", C.c_int32),
         ("kfactor", C.c_int32),
+        ("pair", C.c_int32),
     ]
 
 

@@ -229,6 +229,22 @@ CASES = [
     ("mc_conv_dgrad", lambda: run_conv_dgrad(4, 32, 32, 256, 128, 256)),
     ("mc_conv_dgrad_bn128", lambda: run_conv_dgrad(2, 32, 32, 128, 192, 128)),
     ("mc_conv_wgrad", lambda: run_conv_wgrad(4, 32, 32, 256, 512, 256, nsplit=4)),
+    # long contractions on wide tiles: the one-tile kernel's CTA pairs (cta_group::2, M = 256 instructions; MDM_GEMM_PAIR)
+    ("pair_kk_bigK", lambda: run_plain(512, 512, 4608, 0, 0, 256, bias=True)),
+    ("pair_kk_bn192_odd_m", lambda: run_plain(128 * 3 + 5, 384, 3200, 0, 0, 192, bias=True, residual=True, f16_out=True)),
+    ("pair_kk_bn128", lambda: run_plain(512, 256, 3200, 0, 0, 128, act=True, f16_out=True)),
+    ("pair_kmn_bigK", lambda: run_plain(512, 512, 3200, 0, 1, 256)),
+    ("pair_kmn_bn192", lambda: run_plain(512, 384, 3200, 0, 1, 192)),
+    ("pair_mnk_bigK", lambda: run_plain(512, 256, 3200, 1, 0, 256)),
+    ("pair_kk_batched_bigK", lambda: run_plain(256, 256, 3200, 0, 0, 256, nz1=2, nz2=2)),
+    ("pair_conv_fwd_768", lambda: run_conv_fwd(4, 16, 16, 768, 768, 256)),
+    ("pair_conv_fwd_768_bn192_odd", lambda: run_conv_fwd(3, 8, 24, 768, 768, 192)),
+    ("pair_conv_dgrad_768", lambda: run_conv_dgrad(4, 16, 16, 768, 768, 256)),
+    ("pair_conv_wgrad_768", lambda: run_conv_wgrad(8, 16, 16, 768, 768, 256, nsplit=4)),
+    ("pair_conv_wgrad_384_bn128", lambda: run_conv_wgrad(4, 16, 16, 128, 384, 128, nsplit=2)),
+    ("pair_conv_dgrad_768_bn192", lambda: run_conv_dgrad(3, 8, 24, 768, 768, 192)),
+    ("pair_conv_wgrad_cin192", lambda: run_conv_wgrad(4, 16, 16, 192, 256, 192, nsplit=2)),
+    ("pair_conv_wgrad_long", lambda: run_conv_wgrad(16, 16, 16, 256, 256, 256, nsplit=1)),
     # narrow layers (the 32/64-channel levels of the 256/1024-px nests): 256-pixel stages, one A slab when M <= 64
     ("conv_wgrad_tall_c32", lambda: run_conv_wgrad(2, 64, 64, 32, 32, 32, nsplit=4, kfactor=4)),
     ("conv_wgrad_tall_c64", lambda: run_conv_wgrad(3, 32, 48, 64, 64, 64, nsplit=3, kfactor=4)),
