@@ -80,6 +80,8 @@ typedef struct mdm_gemm_params {
   int32_t pair; /* filled by the launcher: 1 = CTA pairs (tcgen05 cta_group::2). Two adjacent M tiles run as one
                  * M = 256 instruction: each CTA stages its 128 rows of A and HALF of the B tile, so the shared-memory
                  * traffic per flop drops by a third -- what bounds the one-CTA form on wide tiles. */
+  int32_t epi_op; /* filled by the launcher (persistent form): 1 = the fp32 residual tile, 2 = the fp16 GELU' source tile
+                   * is TMA-loaded into the epilogue's staging tile instead of being read row by row from global memory. */
 } mdm_gemm_params;
 
 /* Measurement aid for bench.py's roofline leg: while enabled every launch of the tcgen05 GEMM kernel

@@ -39,18 +39,23 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                           const __grid_constant__ CUtensorMap tmOact, const __grid_constant__ CUtensorMap tmBpart,
-                          const GemmParams p, int m_tiles, int n_tiles, int num_tiles, int staging_bytes) {
+                          const __grid_constant__ CUtensorMap tmOp, const GemmParams p, int m_tiles, int n_tiles,
+                          int num_tiles, int staging_bytes) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t op_bar[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[256];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem;                  // epilogue staging first (fixed size), pipeline stages after it
-  uint8_t* stages = smem + staging_bytes;
+  // epilogue staging first (one buffer of staging_bytes, or two when the epilogue operand comes in by TMA -- see the
+  // epilogue warps), pipeline stages after it
+  const int epi_op = p.epi_op;  // 0 none, 1 residual (fp32, lands in the fp32 staging tile), 2 GELU' source (fp16 tile)
+  uint8_t* staging = smem;
+  uint8_t* stages = smem + (epi_op ? 2 : 1) * staging_bytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nb_alloc = B_MN ? ((p.block_n + 63) / 64) * 64 : p.block_n;
@@ -73,6 +78,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 16);  // one arrival per epilogue warp
+      mbar_init(&op_bar[a], 1);
     }
     fence_barrier_init();
   }
@@ -217,6 +223,179 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev);
     const int ngroups = (p.block_n + 63) / 64;
     int it = 0;
+    if (epi_op != 0) {
+      // ---- epilogue whose fp32 residual / fp16 GELU' source tile comes in by TMA
+      // A thread owns a ROW of the tile, so reading the operand straight from global memory makes every warp request
+      // touch 32 different lines (measured: + 23 us on a 16384 x 768 x 768 launch for a 50 MB residual, + 60 us on
+      // 16384 x 3072 x 768 for the 100 MB GELU' source). Instead thread et == 0 TMA-loads the operand tile of the NEXT
+      // 64-column group into the staging tile that group's results will be written to (same box geometry, same 128B
+      // swizzle); each thread then reads, combines and overwrites its own 64 bytes in place, and the tile leaves by TMA
+      // store as before. Two staging buffers alternate, so a load is one whole group ahead of its use and the store of
+      // group G overlaps the work of group G + 1 (one CTA-wide barrier per group instead of two).
+      auto origin = [&](int tile, int& on0, int& o1, int& o2, int& o3) {
+        const TileCoord tc = decode(tile);
+        on0 = tc.n_tile * p.block_n;
+        if (p.kind == GEMM_CONV) {
+          const int ttw = tc.m_tile % p.tiles_w;
+          const int t = tc.m_tile / p.tiles_w;
+          o1 = ttw * p.PW; o2 = (t % p.tiles_h) * p.PH; o3 = t / p.tiles_h;
+        } else {
+          o1 = tc.m_tile * BLOCK_M; o2 = tc.z1; o3 = tc.z2;
+        }
+      };
+      auto load_op = [&](int tile, int g, int b) {  // thread et == 0
+        int on0, o1, o2, o3;
+        origin(tile, on0, o1, o2, o3);
+        const int colg = on0 + g * 64;
+        if (colg >= p.N) return;
+        uint8_t* buf = staging + b * staging_bytes;
+        if (epi_op == 1) {
+          const bool two = colg + 32 < p.N && g * 64 + 32 < p.block_n;
+          mbar_expect_tx(&op_bar[b], two ? 32768u : 16384u);
+          tma_load_4d(buf, &tmOp, &op_bar[b], colg, o1, o2, o3);
+          if (two) tma_load_4d(buf + 16384, &tmOp, &op_bar[b], colg + 32, o1, o2, o3);
+        } else {
+          mbar_expect_tx(&op_bar[b], 16384u);
+          tma_load_4d(buf + (p.out_f32 != nullptr ? 32768 : 0), &tmOp, &op_bar[b], colg, o1, o2, o3);
+        }
+      };
+      int G = 0;                    // running group index of this CTA; staging buffer G & 1
+      uint32_t uses0 = 0, uses1 = 0;  // operand loads waited for so far, per buffer (parity of the next wait)
+      if (et == 0 && static_cast<int>(blockIdx.x) < num_tiles) load_op(blockIdx.x, 0, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1;
+        int n0, oc1, oc2, oc3;
+        origin(tile, n0, oc1, oc2, oc3);
+        // bias tile (the previous tile's readers are past its last group barrier)
+        epi_bar_sync();
+        if (et < 256) s_bias[et] = (p.bias != nullptr && et < p.block_n && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+        epi_bar_sync();
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        for (int g = 0; g < ngroups; ++g, ++G) {
+          const int b = G & 1;
+          uint8_t* buf = staging + b * staging_bytes;
+          uint8_t* b32 = buf;
+          uint8_t* b16 = buf + (p.out_f32 != nullptr ? 32768 : 0);
+          uint8_t* bact = b16 + (p.out_f16 != nullptr ? 16384 : 0);
+          const int cidx = g * 64 + quarter * 16;
+          const bool live = cidx < p.block_n;  // warp-uniform
+          const int colg = n0 + g * 64;
+          const bool has_op = colg < p.N;       // CTA-uniform
+          float v[16];
+          if (live) {
+            tmem_ld16(taddr_row + static_cast<uint32_t>(cidx), v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = *reinterpret_cast<const float4*>(&s_bias[cidx + 4 * q]);
+              v[4 * q + 0] = fmaf(v[4 * q + 0], alpha, bq.x);
+              v[4 * q + 1] = fmaf(v[4 * q + 1], alpha, bq.y);
+              v[4 * q + 2] = fmaf(v[4 * q + 2], alpha, bq.z);
+              v[4 * q + 3] = fmaf(v[4 * q + 3], alpha, bq.w);
+            }
+          }
+          if (g == ngroups - 1) {
+            // last TMEM read of this tile is done: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          if (et == 0) {
+            bulk_wait_read();  // the store of group G - 1 has left the other buffer
+            int nt = tile, ng = g + 1;
+            if (ng == ngroups) {
+              nt = tile + gridDim.x;
+              ng = 0;
+            }
+            if (nt < num_tiles) load_op(nt, ng, b ^ 1);
+          }
+          if (has_op) {
+            if (b == 0) mbar_wait(&op_bar[0], uses0++ & 1u);
+            else mbar_wait(&op_bar[1], uses1++ & 1u);
+          }
+          if (live) {
+            const int cc = quarter;
+            if (epi_op == 1) {
+              uint8_t* base = b32 + (cc >> 1) * 16384 + r * 128;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float4* slot = reinterpret_cast<float4*>(base + ((static_cast<uint32_t>((cc & 1) * 4 + q) ^ swz) * 16));
+                if (has_op) {
+                  const float4 t = *slot;
+                  v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+                *slot = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            } else {
+              uint8_t* base = b16 + r * 128;
+              uint4* s0 = reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16));
+              uint4* s1 = reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16));
+              if (has_op) {
+                const uint4 u0 = *s0, u1 = *s1;
+                const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
+                const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 a = __half22float2(h0[q]), b2 = __half22float2(h1[q]);
+                  v[2 * q] *= gelu_grad(a.x);
+                  v[2 * q + 1] *= gelu_grad(a.y);
+                  v[8 + 2 * q] *= gelu_grad(b2.x);
+                  v[8 + 2 * q + 1] *= gelu_grad(b2.y);
+                }
+              }
+              __half2 h16[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) h16[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+              *s0 = *reinterpret_cast<uint4*>(&h16[0]);
+              *s1 = *reinterpret_cast<uint4*>(&h16[4]);
+              if (p.out_f32 != nullptr) {
+                uint8_t* base32 = b32 + (cc >> 1) * 16384 + r * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(base32 + ((static_cast<uint32_t>((cc & 1) * 4 + q) ^ swz) * 16)) =
+                      make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            }
+            if (epi_op == 1 && p.out_f16 != nullptr) {
+              __half2 h16[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) h16[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+              uint8_t* base = b16 + r * 128;
+              *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h16[0]);
+              *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&h16[4]);
+            }
+            if (p.out_act_f16 != nullptr) {
+              __half2 hact[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float a0 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q]) : v[2 * q];
+                const float a1 = (p.act == ACT_GELU) ? gelu_erf(v[2 * q + 1]) : v[2 * q + 1];
+                hact[q] = __floats2half2_rn(a0, a1);
+              }
+              uint8_t* base = bact + r * 128;
+              *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&hact[0]);
+              *reinterpret_cast<uint4*>(base + ((static_cast<uint32_t>(cc * 2 + 1) ^ swz) * 16)) = *reinterpret_cast<uint4*>(&hact[4]);
+            }
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (et == 0) {
+            if (colg < p.N) {
+              if (p.out_f32 != nullptr) {
+                tma_store_4d(&tmO32, b32, colg, oc1, oc2, oc3);
+                if (colg + 32 < p.N && g * 64 + 32 < p.block_n) tma_store_4d(&tmO32, b32 + 16384, colg + 32, oc1, oc2, oc3);
+              }
+              if (p.out_f16 != nullptr) tma_store_4d(&tmO16, b16, colg, oc1, oc2, oc3);
+              if (p.out_act_f16 != nullptr) tma_store_4d(&tmOact, bact, colg, oc1, oc2, oc3);
+            }
+            bulk_commit();
+          }
+        }
+      }
+      if (et == 0) bulk_wait_all();
+    } else {
     bool stores_pending = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const TileCoord c = decode(tile);
@@ -397,6 +576,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
     if (et == 0) bulk_wait_all();
+    }  // legacy (operand from global memory) epilogue
   }
   tc_fence_before();
   __syncthreads();
@@ -406,7 +586,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
 template <bool A_MN, bool B_MN>
 int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap& tmBpart,
-             const GemmParams& p, int m_tiles, int n_tiles, int num_tiles, int grid, size_t smem, int staging_bytes,
+             const CUtensorMap& tmOp, const GemmParams& p, int m_tiles, int n_tiles, int num_tiles, int grid, size_t smem, int staging_bytes,
              cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -435,11 +615,11 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_persistent_kernel<A_MN, B_MN>, tmA, tmB, tmO[0], tmO[1], tmO[2],
-                                        tmBpart, p, m_tiles, n_tiles, num_tiles, staging_bytes);
+                                        tmBpart, tmOp, p, m_tiles, n_tiles, num_tiles, staging_bytes);
     if (le != cudaSuccess) return static_cast<int>(le);
   } else {
-    gemm_tc_persistent_kernel<A_MN, B_MN><<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, p,
-                                                                           m_tiles, n_tiles, num_tiles, staging_bytes);
+    gemm_tc_persistent_kernel<A_MN, B_MN><<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO[0], tmO[1], tmO[2], tmBpart, tmOp,
+                                                                           p, m_tiles, n_tiles, num_tiles, staging_bytes);
   }
   if (g_profile) {
     cudaEventRecord(e1, stream);
@@ -455,16 +635,18 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* 
 
 // Called by launch_gemm when the launch is eligible (no split-K, TMA-store epilogue, not wgrad).
 int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO,
-                           const CUtensorMap& tmBpart, int cluster, int a_mn, int b_mn, GemmParams p, int m_tiles,
-                           int n_tiles, cudaStream_t stream) {
+                           const CUtensorMap& tmBpart, const CUtensorMap& tmOp, int cluster, int a_mn, int b_mn,
+                           GemmParams p, int m_tiles, int n_tiles, cudaStream_t stream) {
   const int nb_alloc = b_mn ? ((p.block_n + 63) / 64) * 64 : p.block_n;
   const int stage_bytes = A_STAGE_BYTES + nb_alloc * 128;
-  const int staging = (p.out_f32 ? 32768 : 0) + (p.out_f16 ? 16384 : 0) + (p.out_act_f16 ? 16384 : 0);
-  int stages = (222 * 1024 - staging - 1024) / stage_bytes;
+  const int staging = (p.out_f32 ? 32768 : 0) + (p.out_f16 ? 16384 : 0) + (p.out_act_f16 ? 16384 : 0);  // one buffer
+  if (p.epi_op != 0 && (222 * 1024 - 2 * staging - 1024) / stage_bytes < 3) p.epi_op = 0;  // keep a 3-stage pipeline
+  const int nbuf = p.epi_op != 0 ? 2 : 1;
+  int stages = (222 * 1024 - nbuf * staging - 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return -30;
   p.num_stages = stages;
-  const size_t smem = static_cast<size_t>(staging) + static_cast<size_t>(stages) * stage_bytes + 1024;
+  const size_t smem = static_cast<size_t>(nbuf) * staging + static_cast<size_t>(stages) * stage_bytes + 1024;
   p.cluster = cluster > 1 ? cluster : 1;
   if (p.cluster > 1) m_tiles = (m_tiles + p.cluster - 1) / p.cluster * p.cluster;  // ghost tiles store nothing
   const int num_tiles = m_tiles * n_tiles * p.nz1 * p.nz2;
@@ -473,12 +655,12 @@ int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   const int sms = (148 - g_sm_reserve) / p.cluster * p.cluster;
   const int grid = num_tiles < sms ? num_tiles : sms;  // (num_tiles is a multiple of the cluster size)
   if (!a_mn && !b_mn)
-    return launch_p<false, false>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+    return launch_p<false, false>(tmA, tmB, tmO, tmBpart, tmOp, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
   if (!a_mn && b_mn)
-    return launch_p<false, true>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+    return launch_p<false, true>(tmA, tmB, tmO, tmBpart, tmOp, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
   if (a_mn && b_mn)
-    return launch_p<true, true>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
-  return launch_p<true, false>(tmA, tmB, tmO, tmBpart, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+    return launch_p<true, true>(tmA, tmB, tmO, tmBpart, tmOp, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
+  return launch_p<true, false>(tmA, tmB, tmO, tmBpart, tmOp, p, m_tiles, n_tiles, num_tiles, grid, smem, staging, stream);
 }
 
 }  // namespace mdm

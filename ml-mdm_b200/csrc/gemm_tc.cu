@@ -718,8 +718,10 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
 
   // ---- staged (TMA-store) epilogue when the output geometry allows it
   alignas(64) CUtensorMap tmO[3];
+  alignas(64) CUtensorMap tmOp = tmA;  // epilogue operand (residual / GELU' source) of the persistent form
   tmO[0] = tmO[1] = tmO[2] = tmA;
   p.epi_tma = 0;
+  p.epi_op = 0;
   {
     auto ok = [&](const void* ptr, int esz) {
       if (ptr == nullptr) return true;
@@ -758,6 +760,15 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
       if (p.out_f16 != nullptr) good = good && encode_tmap(&tmO[1], mk(p.out_f16, 2, 64), false) == 0;
       if (p.out_act_f16 != nullptr) good = good && encode_tmap(&tmO[2], mk(p.out_act_f16, 2, 64), false) == 0;
       if (good) {
+        // the persistent form can take its epilogue operand by TMA into the staging tile (gemm_persistent.cu)
+        static const bool op_tma = getenv("MDM_EPI_OP_TMA") == nullptr || atoi(getenv("MDM_EPI_OP_TMA")) != 0;
+        if (op_tma && persist_shape && !p.atomic) {
+          if (p.residual != nullptr && p.out_f32 != nullptr && p.gelu_grad_src == nullptr && ok(p.residual, 4)) {
+            if (encode_tmap(&tmOp, mk(const_cast<float*>(p.residual), 4, 32), true) == 0) p.epi_op = 1;
+          } else if (p.gelu_grad_src != nullptr && p.out_f16 != nullptr && p.residual == nullptr && ok(p.gelu_grad_src, 2)) {
+            if (encode_tmap(&tmOp, mk(const_cast<void*>(p.gelu_grad_src), 2, 64), false) == 0) p.epi_op = 2;
+          }
+        }
         p.epi_tma = 1;
         const size_t need = (p.out_f32 ? 32768 : 0) + (p.out_f16 ? 16384 : 0) + (p.out_act_f16 ? 16384 : 0) + 1024;
         if (smem < need) smem = need;
@@ -787,9 +798,10 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   }
   p.cluster = 1;
 
+  p.epi_op = (persist_shape && p.epi_tma) ? p.epi_op : 0;
   if (persist_shape && p.epi_tma) {
     p.pair = 0;
-    return launch_gemm_persistent(tmA, tmB, tmO, tmBpart, cs, a_mn, b_mn, p, m_tiles, n_tiles, stream);
+    return launch_gemm_persistent(tmA, tmB, tmO, tmBpart, tmOp, cs, a_mn, b_mn, p, m_tiles, n_tiles, stream);
   }
 
   if (p.pair) {

@@ -40,8 +40,8 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
                 cudaStream_t stream);
 
 int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO,
-                           const CUtensorMap& tmBpart, int cluster, int a_mn, int b_mn, GemmParams p, int m_tiles,
-                           int n_tiles, cudaStream_t stream);
+                           const CUtensorMap& tmBpart, const CUtensorMap& tmOp, int cluster, int a_mn, int b_mn,
+                           GemmParams p, int m_tiles, int n_tiles, cudaStream_t stream);
 
 // Counts kernel launches issued by this library (bench.py reports it as gpu_launches).
 extern unsigned long long g_launch_count;

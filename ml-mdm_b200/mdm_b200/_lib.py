@@ -66,6 +66,7 @@ class GemmParams(C.Structure):
         ("cluster", C.c_int32),
         ("kfactor", C.c_int32),
         ("pair", C.c_int32),
+        ("epi_op", C.c_int32),
     ]
 
 

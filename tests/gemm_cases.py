@@ -16,7 +16,7 @@ def _stream():
 
 
 def run_plain(M, N, K, a_mn, b_mn, block_n, nz1=1, nz2=1, bias=False, residual=False, act=False,
-              f16_out=False, nsplit=1, alpha=1.0, seed=0):
+              f16_out=False, nsplit=1, alpha=1.0, seed=0, ggrad=False, f32_out=True):
     """C[z2,z1] = alpha * A @ B^T (+bias) (+residual); operands stored K-major or MN-major."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     nb = nz1 * nz2
@@ -54,8 +54,14 @@ def run_plain(M, N, K, a_mn, b_mn, block_n, nz1=1, nz2=1, bias=False, residual=F
         res_t = torch.randn(nb, M, N, generator=g).to(DEV)
         p.residual = res_t.data_ptr()
         ref = ref + res_t
+    if ggrad:  # FFN backward epilogue: result *= gelu'(src), src indexed like the output
+        src = (torch.randn(nb, M, N, generator=g) * 1.5).to(torch.float16).to(DEV)
+        p.gelu_grad_src = src.data_ptr()
+        x = src.float()
+        ref = ref * (0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5)
     out32 = torch.zeros(nb, M, N, device=DEV)
-    p.out_f32 = out32.data_ptr()
+    if f32_out:
+        p.out_f32 = out32.data_ptr()
     out16 = outact = None
     if f16_out:
         out16 = torch.zeros(nb, M, N, device=DEV, dtype=torch.float16)
@@ -68,7 +74,7 @@ def run_plain(M, N, K, a_mn, b_mn, block_n, nz1=1, nz2=1, bias=False, residual=F
         p.atomic = 1
     _lib.gemm_raw(sa, sb, a_mn, b_mn, p, _stream())
     torch.cuda.synchronize()
-    errs = {"f32": rel_err(out32, ref)}
+    errs = {"f32": rel_err(out32, ref)} if f32_out else {}
     if f16_out:
         errs["f16"] = rel_err(out16.float(), ref)
     if act:
@@ -91,7 +97,7 @@ def conv_geometry(H, W):
     return PW
 
 
-def run_conv_fwd(nimg, H, W, Cin, Cout, block_n, bias=True, seed=0):
+def run_conv_fwd(nimg, H, W, Cin, Cout, block_n, bias=True, seed=0, residual=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = (torch.randn(nimg, H, W, Cin, generator=g) * 0.5).to(torch.float16).to(DEV)  # NHWC
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1)
@@ -119,6 +125,10 @@ def run_conv_fwd(nimg, H, W, Cin, Cout, block_n, bias=True, seed=0):
         p.bias = b.data_ptr()
     out = torch.zeros(nimg, H, W, Cout, device=DEV)
     p.out_f32 = out.data_ptr()
+    if residual:
+        res = torch.randn(nimg, H, W, Cout, generator=g).to(DEV)
+        p.residual = res.data_ptr()
+        ref = ref + res
     _lib.gemm_raw(sa, sb, 0, 0, p, _stream())
     torch.cuda.synchronize()
     return {"f32": rel_err(out, ref)}
@@ -245,6 +255,15 @@ CASES = [
     ("pair_conv_dgrad_768_bn192", lambda: run_conv_dgrad(3, 8, 24, 768, 768, 192)),
     ("pair_conv_wgrad_cin192", lambda: run_conv_wgrad(4, 16, 16, 192, 256, 192, nsplit=2)),
     ("pair_conv_wgrad_long", lambda: run_conv_wgrad(16, 16, 16, 256, 256, 256, nsplit=1)),
+    # persistent form with the epilogue operand (fp32 residual / fp16 GELU' source) TMA-loaded into the staging tile
+    ("op_res_many_tiles", lambda: run_plain(128 * 80 + 3, 768, 256, 0, 0, 192, bias=True, residual=True)),
+    ("op_res_partial_n", lambda: run_plain(128 * 9, 320 + 40, 128, 0, 0, 256, bias=True, residual=True, f16_out=True)),
+    ("op_res_bn96_batched", lambda: run_plain(260, 96, 192, 0, 0, 96, nz1=3, nz2=2, residual=True, act=True, f16_out=True)),
+    ("op_res_conv", lambda: run_conv_fwd(6, 32, 32, 128, 256, 256, residual=True)),
+    ("op_res_conv_ragged", lambda: run_conv_fwd(3, 24, 40, 64, 192, 192, residual=True)),
+    ("op_ggrad_f16", lambda: run_plain(128 * 80, 768, 256, 0, 1, 192, f16_out=True, ggrad=True, f32_out=False)),
+    ("op_ggrad_f16_f32_ragged", lambda: run_plain(128 * 5 + 77, 640 + 24, 192, 0, 1, 256, f16_out=True, ggrad=True)),
+    ("ggrad_one_tile", lambda: run_plain(512, 256, 3200, 0, 1, 256, f16_out=True, ggrad=True)),
     # narrow layers (the 32/64-channel levels of the 256/1024-px nests): 256-pixel stages, one A slab when M <= 64
     ("conv_wgrad_tall_c32", lambda: run_conv_wgrad(2, 64, 64, 32, 32, 32, nsplit=4, kfactor=4)),
     ("conv_wgrad_tall_c64", lambda: run_conv_wgrad(3, 32, 48, 64, 64, 64, nsplit=3, kfactor=4)),
