@@ -677,8 +677,14 @@ int launch_gemm(const TmapSpec& A, const TmapSpec& B, int a_mn, int b_mn, const 
   static const int persist_min_n = getenv("MDM_PERSIST_MIN_N") ? atoi(getenv("MDM_PERSIST_MIN_N")) : 96;
   const long long ntiles = static_cast<long long>(m_tiles) * n_tiles * p.nz1 * p.nz2;
   const bool rounds_ok = ntiles <= 148 || ntiles >= 296;
+  // With CTA pairs in the one-tile form the crossover moved down for the linears: K >= 2304 is faster there (fc1 data
+  // gradient 16384x768x3072 2.67 -> 2.17 ms per step, qkv data gradient 2.07 -> 1.78, fc2 forward 3.02 -> 2.64), K = 1536
+  // with a GELU' epilogue is not (1.76 -> 2.26), and the 36-k-block 3x3 convs stay (2.21 vs 2.34):
+  // profiles/r02_persist_kb_sweep.txt.
+  static const int persist_max_kb = getenv("MDM_PERSIST_MAX_KBLOCKS") ? atoi(getenv("MDM_PERSIST_MAX_KBLOCKS")) : 0;
+  const int max_kb = persist_max_kb > 0 ? persist_max_kb : (p.kind == GEMM_PLAIN ? 35 : 48);
   const bool persist_shape = persistent && p.block_n >= persist_min_n && p.nsplit == 1 && p.kind != GEMM_CONV_WGRAD &&
-                             p.num_kblocks <= 48 && rounds_ok;  // (and a TMA-store epilogue, checked below)
+                             p.num_kblocks <= max_kb && rounds_ok;  // (and a TMA-store epilogue, checked below)
 
   // ---- CTA pairs (cta_group::2) for the MMA-bound launches of the one-tile form: wide tiles, long contraction.
   // Each CTA stages 128 rows of A and HALF of the B tile; the leader issues M = 256 instructions for both.
