@@ -81,6 +81,10 @@ def bench(name, M, N, K, b_mn, bn, bias=True, res=False, f32=False, f16=False, a
 
 def main(M):
     C = 768
+    if "--ncu" in sys.argv:  # the two TMA-operand epilogues, a few launches each, for an `ncu --set full` capture
+        bench("proj fwd: res + f32 (train)", M, C, C, 0, 192, res=True, f32=True, iters=1)
+        bench("fc2 dgrad: f16 * gelu'(src) (train)", M, 4 * C, C, 1, 192, bias=False, f16=True, gsrc=True, iters=1)
+        return
     for bn in (192, 256, 128):
         bench("fc1 fwd: bias only, f16", M, 4 * C, C, 0, bn, f16=True)
         bench("fc1 fwd: +GELU, act only", M, 4 * C, C, 0, bn, act=True)
@@ -100,4 +104,4 @@ def main(M):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 16384)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 16384)
