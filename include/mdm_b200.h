@@ -33,6 +33,11 @@ typedef void* mdm_stream_t; /* cudaStream_t */
 
 const char* mdm_last_error(void);
 int mdm_version(void);
+/* sizeof() of the structs of this header as the library was compiled (0 = mdm_tmap_spec, 1 = mdm_gemm_params,
+ * 2 = mdm_level_cfg, 3 = mdm_net_cfg, 4 = mdm_net_io, 5 = mdm_net_grad_io, 6 = mdm_opt_chunk, 7 = mdm_adam_cfg; -1 for
+ * anything else): a binding written in another language (the ctypes mirror in mdm_b200/, a cgo / JNI stub) checks its own
+ * struct layout against this instead of trusting that two copies of a declaration stayed in step. */
+long long mdm_abi_sizeof(int which);
 /* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long mdm_launch_count(void);
 

@@ -69,6 +69,20 @@ int mdm_profile_read(double* total_ms, long long* launches) {
   return 0;
 }
 
+long long mdm_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return static_cast<long long>(sizeof(mdm_tmap_spec));
+    case 1: return static_cast<long long>(sizeof(mdm_gemm_params));
+    case 2: return static_cast<long long>(sizeof(mdm_level_cfg));
+    case 3: return static_cast<long long>(sizeof(mdm_net_cfg));
+    case 4: return static_cast<long long>(sizeof(mdm_net_io));
+    case 5: return static_cast<long long>(sizeof(mdm_net_grad_io));
+    case 6: return static_cast<long long>(sizeof(mdm_opt_chunk));
+    case 7: return static_cast<long long>(sizeof(mdm_adam_cfg));
+    default: return -1;
+  }
+}
+
 int mdm_gemm_raw(const mdm_tmap_spec* A, const mdm_tmap_spec* B, int a_mn, int b_mn,
                  const mdm_gemm_params* p, mdm_stream_t stream) {
   int rc = mdm::launch_gemm(*A, *B, a_mn, b_mn, *p, static_cast<cudaStream_t>(stream));

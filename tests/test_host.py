@@ -70,6 +70,34 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.mdm_version() >= 100
 
 
+def test_ctypes_mirrors_match_the_compiled_struct_layouts():
+    """Every ctypes.Structure that mirrors a struct of include/mdm_b200.h has the size the library was compiled with
+    (a field added on one side only would otherwise shift every later field silently)."""
+    from mdm_b200 import optim
+    from mdm_b200.models import native
+
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.mdm_abi_sizeof.restype = ctypes.c_longlong
+    mirrors = [_lib.TmapSpec, _lib.GemmParams, native.LevelCfg, native.NetCfg, native.NetIO, native.NetGradIO,
+               optim.OptChunk, optim.AdamCfg]
+    for which, cls in enumerate(mirrors):
+        assert lib.mdm_abi_sizeof(which) == ctypes.sizeof(cls), (which, cls.__name__)
+    assert lib.mdm_abi_sizeof(len(mirrors)) == -1
+    # and the field NAMES of the two largest ones, in order, against the header text
+    hdr = open(os.path.join(ROOT, "include", "mdm_b200.h")).read()
+    for cname, cls in (("mdm_gemm_params", _lib.GemmParams), ("mdm_net_io", native.NetIO)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*\]", "", part.strip().split()[-1].lstrip("*")))
+        assert names == [f[0] for f in cls._fields_], (cname, names, [f[0] for f in cls._fields_])
+
+
 def test_compute_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
